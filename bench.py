@@ -1,0 +1,278 @@
+#!/usr/bin/env python
+"""bench.py — tokens/s of the episodic-LSTM training step (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # our CUDA engine
+    python bench.py --impl reference --steps 3 --warmup 1          # reference CPU path (oracle port)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU, NCCL
+
+A "step" is one full optimizer step (fwd + bwd + [all-reduce] + clip + Adam) on one batch of
+synthetic 5-shot lyrics episodes: BASELINE.json configs[1] — vocab 10k, seq_len 128, E=H=512,
+32 episodes (1440 sequences) per step per GPU (weak scaling).  One JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+PKG = ROOT / "few-shot-music-generation_b200"
+for p in (str(ROOT), str(PKG), str(PKG / "src")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: model/data dims + episodes per step per GPU
+    "lyrics5shot_v10k_t128_h512": dict(input_size=10000, embedding_size=512, hidden_size=512, n_layers=1, max_len=128,
+                                        episodes=32, kind="zipf"),
+    "midi5shot_v4708_t256_h1024": dict(input_size=4708, embedding_size=1024, hidden_size=1024, n_layers=1, max_len=256,
+                                        episodes=1, kind="uniform"),
+    "lyrics5shot_cpu_ref_t32_h128": dict(input_size=10000, embedding_size=250, hidden_size=128, n_layers=1, max_len=32,
+                                          episodes=1, kind="zipf"),
+}
+SEQS_PER_EPISODE = 5 * (5 + 4)  # batch_size * (support + query), reference 5shot.yaml + lstm_baseline.yaml:15
+
+
+def model_config(w: dict) -> dict:
+    return dict(name="lstm_baseline", model_module_name="models.lstm_baseline", model_class_name="LSTMBaseline",
+                input_size=w["input_size"], embedding_size=w["embedding_size"], hidden_size=w["hidden_size"],
+                n_layers=w["n_layers"], max_len=w["max_len"], lr=5e-3, n_decay=10000, max_grad_norm=5, batch_size=5,
+                support_size=5, query_size=4, seed=1234, tensorboard=False)
+
+
+def flops_per_token(w: dict) -> float:
+    """ALGORITHMIC training FLOPs/token: 3 * (2(E+H)4H + 2 H V')."""
+    e, h, v1 = w["embedding_size"], w["hidden_size"], w["input_size"] + 1
+    return 3.0 * (2.0 * (e + h) * 4 * h + 2.0 * h * v1)
+
+
+def peaks() -> dict:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return dict(tflops=d.get("bf16_tflops_sustained", 1422.7), tflops_burst=d.get("bf16_tflops", 1696.7),
+                    hbm=d.get("hbm_gbs", 6569.6), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(self.rows))
+
+
+def synthetic_batches(w: dict, n_batches: int, seed: int):
+    from oracle import lstm_oracle as O  # synthetic-input generator only (shared with the tests)
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n_batches):
+        rows = []
+        for _ in range(w["episodes"]):
+            sup, qry = O.synthetic_episode(rng, 5, 5, 4, w["max_len"], w["input_size"], w["kind"])
+            rows.append((sup, qry))
+        out.append(rows)
+    return out
+
+
+def cpu_reference_steps(w: dict, steps: int, warmup: int, episodes: int):
+    """The reference's CPU path (oracle port: torch-CPU fp32 restatement, all host threads) on a
+    bounded sample: `episodes` episodes of the workload's dims per step."""
+    import torch
+    from oracle import lstm_oracle as O
+    from oracle.torch_ref import TorchRef
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = model_config(w)
+    ref = TorchRef(O.glorot_init(cfg, 1234), cfg, torch.float32)
+    wl = dict(w, episodes=episodes)
+    batches = synthetic_batches(wl, steps + warmup, 1234)
+    toks = [np.concatenate([O.episode_train_tokens(s, q) for s, q in b]) for b in batches]
+    for i in range(warmup):
+        ref.train_step(toks[i])
+    t0 = time.perf_counter()
+    for i in range(warmup, warmup + steps):
+        ref.train_step(toks[i])
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    n_tok = toks[0].size
+    return n_tok / dt, dt * 1e3, cores, n_tok
+
+
+def run_reference(args, w, wname):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tps, ms, cores, n_tok = cpu_reference_steps(w, args.steps, max(args.warmup, 1), episodes=1)
+    sample = f"1 episode ({n_tok} tokens) of {wname} per step, torch-CPU fp32 restatement of the reference (TensorFlow 1.x not installable)"
+    line = dict(impl="reference", metric="tokens/sec (5-shot lyrics, seq=128) training step", value=tps, unit="tokens/s",
+                n_gpus=args.gpus, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wname, global_batch_seqs=SEQS_PER_EPISODE, seq_len=w["max_len"], sample=sample),
+                cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lyrics5shot_v10k_t128_h512", choices=sorted(WORKLOADS))
+    ap.add_argument("--episodes", type=int, default=0, help="override episodes/step/GPU (debug; invalidates the number)")
+    ap.add_argument("--flags", type=int, default=0, help="FSMG_FLAG_* bits (debug routes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wname = args.workload
+    w = dict(WORKLOADS[wname])
+    if args.episodes:
+        w["episodes"] = args.episodes
+    if args.impl == "reference":
+        return run_reference(args, w, wname)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    args.warmup = max(args.warmup, 3)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from train.train import load_model_from_config
+    cfg = model_config(w)
+    cfg["episodes_per_step"] = w["episodes"]
+    cfg["fsmg_flags"] = args.flags
+    model = load_model_from_config(cfg)     # the reference's plugin registry -> models.lstm_baseline.LSTMBaseline
+    model.recover_or_init("")                # Glorot-uniform from seed 1234, identical on every rank
+    eng = model.engine
+    n_seqs = SEQS_PER_EPISODE * w["episodes"]
+    T = w["max_len"]
+    tokens_per_step = n_seqs * T * world
+
+    total = args.warmup + args.steps
+    n_distinct = min(total, 4)
+    batches = synthetic_batches(w, n_distinct, 1234 + rank)
+
+    class Ep:
+        def __init__(self, s, q):
+            self.support, self.query = s, q
+    host_batches = [[Ep(s, q) for s, q in b] for b in batches]
+    dev_batches = [torch.from_numpy(model._train_tokens(hb).astype(np.int32)).to(f"cuda:{local}") for hb in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- device-resident arm: `value` ----------------------------------------------------------------
+    for i in range(args.warmup):
+        eng.train_step_device(dev_batches[i % n_distinct])
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        eng.train_step_device(dev_batches[(args.warmup + i) % n_distinct])
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    value = tokens_per_step / (ms_step * 1e-3)
+    launches = eng.last_launch_count()
+
+    # ---- end-to-end arm through the plugin API with HOST buffers: `e2e` ------------------------------
+    for i in range(2):
+        model.train(host_batches[i % n_distinct])
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        model.train(host_batches[i % n_distinct])   # numpy in -> pinned -> H2D -> step -> D2H loss -> float
+    ev1.record()
+    barrier()
+    ms_e2e = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    e2e = dict(value=tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
+               h2d_bytes_per_step=n_seqs * T * 4, d2h_bytes_per_step=4)
+
+    pk = peaks()
+    f_tok = flops_per_token(w)
+    achieved = f_tok * (tokens_per_step / world) / (ms_step * 1e-3) / 1e12   # per GPU
+    roofline = dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"],
+                    traffic=None, kernel="whole training step (algorithmic 3*(2(E+H)4H+2HV') FLOP/token)",
+                    peak_source=pk["source"])
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            tps, ms, cores, n_tok = cpu_reference_steps(w, steps=3, warmup=1, episodes=1)
+            cpu = dict(value=tps, unit="tokens/s", cores=cores, kind="port", ms_per_step=ms,
+                       sample=f"3 steps of 1 episode ({n_tok} tokens) at the workload's dims; torch-CPU fp32 restatement "
+                              "(oracle/torch_ref.py) — TensorFlow 1.x reference cannot be installed")
+        line = dict(metric="tokens/sec (5-shot lyrics, seq=128) training step", value=value, unit="tokens/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f16 operands, f32 accumulate/state/optimizer", data="synthetic",
+                    config=dict(workload=wname, episodes_per_step_per_gpu=w["episodes"], global_batch_seqs=n_seqs * world,
+                                seq_len=T, vocab=w["input_size"], hidden=w["hidden_size"], embedding=w["embedding_size"],
+                                parallelism=f"dp{world}", l2="per-step working set (~GBs of activations) >> 126 MB L2; "
+                                f"{n_distinct} distinct batches rotate", flags=args.flags),
+                    e2e=e2e, gpu_launches=int(launches) * args.steps, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

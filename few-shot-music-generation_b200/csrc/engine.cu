@@ -1,0 +1,629 @@
+// engine.cu — libfsmg: handle, workspace layout, orchestration of the episodic-LSTM hot path and
+// the C-ABI declared in include/fsmg.h.
+//
+// Replaces (reference file:line): LSTMBaseline._build_graph + train/eval/sample
+// (src/models/lstm_baseline.py:38-156) and the TensorFlow-1.x runtime underneath it.
+// Data layout in HBM: token index is TIME-MAJOR, r = t*N + n, so that every
+// recurrent step touches one contiguous [N, .] block.
+#include <cuda.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/fsmg.h"
+#include "common.cuh"
+#include "simt_kernels.cuh"
+#include "tc_gemm.cuh"
+
+namespace fsmg {
+
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+int set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error() = buf;
+    return code;
+}
+
+struct LayerBuf {
+    int in = 0, inp = 0;          // input width and its padded leading dimension
+    int64_t k_off = 0, b_off = 0; // offsets into the flat parameter buffer
+    __half* K16 = nullptr;        // [(in+H), G4p]  row-major copy of kernel   (B of dX / dh_rec)
+    __half* WxT16 = nullptr;      // [4H, inp]      transpose of kernel[:in]   (B of the input GEMM)
+    __half* WhT16 = nullptr;      // [4H, Hp]       transpose of kernel[in:]   (B of the recurrent GEMM)
+    __half* gates = nullptr;      // [NT, G4p] post-activation i,j,f,o (stash for BPTT)
+    float* c = nullptr;           // [NT, H]
+    __half* hs = nullptr;         // [NT, Hp]
+};
+
+}  // namespace fsmg
+
+using namespace fsmg;
+
+struct fsmg_handle {
+    fsmg_config cfg;
+    std::string scope;
+    int V = 0, V1 = 0, E = 0, H = 0, L = 0, T = 0, Nmax = 0;
+    int Ep = 0, Hp = 0, G4 = 0, G4p = 0, Vp = 0;
+    std::vector<fsmg_param_info> infos;
+    int64_t n_params = 0;       // padded flat count
+    int64_t emb_off = 0, sw_off = 0, sb_off = 0;
+    int64_t dense_begin = 0;    // first element after the embedding segment
+    std::vector<LayerBuf> layers;
+    // bound buffers
+    float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+    char* ws = nullptr;
+    int64_t ws_bytes = 0, ws_need = 0;
+    bool bound = false;
+    // workspace carve-up
+    int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *samp_ids = nullptr, *samp_out = nullptr;
+    __half *emb16 = nullptr, *Ws16 = nullptr, *WsT16 = nullptr, *xemb = nullptr, *dgates = nullptr, *dlogits = nullptr;
+    float *pre = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
+    float *lse = nullptr, *nll = nullptr, *scalars = nullptr;
+    float *s_x = nullptr, *s_g = nullptr, *s_logits = nullptr;
+    std::vector<float*> s_c, s_h;
+    int chunk_rows = 0;
+    int samp_max = 0;
+    // pinned host staging
+    int32_t* h_tok = nullptr;
+    float* h_scal = nullptr;
+    int64_t h_tok_elems = 0;
+    int64_t launches = 0;
+    fsmg::TcContext tc;
+};
+
+namespace fsmg {
+
+#define LAUNCH_COUNT(h) ((h)->launches++)
+
+// bump allocator used twice: sizing (base == nullptr) and carving
+struct Bump {
+    char* base;
+    int64_t off = 0;
+    template <typename T>
+    T* take(int64_t count) {
+        off = round_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * (int64_t)sizeof(T);
+        return p;
+    }
+};
+
+static void carve(fsmg_handle* h, char* base) {
+    Bump b{base};
+    const int64_t NT = (int64_t)h->Nmax * h->T;
+    h->scalars = b.take<float>(64);
+    h->x_ids = b.take<int32_t>(NT);
+    h->y_ids = b.take<int32_t>(NT);
+    h->tok_stage = b.take<int32_t>(NT);
+    h->emb16 = b.take<__half>((int64_t)h->V1 * h->Ep);
+    h->Ws16 = b.take<__half>((int64_t)h->H * h->Vp);
+    h->WsT16 = b.take<__half>((int64_t)h->V1 * h->Hp);
+    h->xemb = b.take<__half>(NT * h->Ep);
+    h->pre = b.take<float>(NT * h->G4);
+    h->dgates = b.take<__half>(NT * h->G4p);
+    int wmax = h->E > h->H ? h->E : h->H;
+    h->dact[0] = b.take<float>(NT * wmax);
+    h->dact[1] = b.take<float>(NT * wmax);
+    h->dh_rec = b.take<float>((int64_t)h->Nmax * h->H);
+    h->dc_next = b.take<float>((int64_t)h->Nmax * h->H);
+    h->lse = b.take<float>(NT);
+    h->nll = b.take<float>(NT);
+    for (auto& l : h->layers) {
+        l.K16 = b.take<__half>((int64_t)(l.in + h->H) * h->G4p);
+        l.WxT16 = b.take<__half>((int64_t)h->G4 * l.inp);
+        l.WhT16 = b.take<__half>((int64_t)h->G4 * h->Hp);
+        l.gates = b.take<__half>(NT * h->G4p);
+        l.c = b.take<float>(NT * h->H);
+        l.hs = b.take<__half>(NT * h->Hp);
+    }
+    // projection chunk: rows sized so the fp16 logits chunk stays L2-resident (<= ~48 MB)
+    int64_t rows = (48ll << 20) / ((int64_t)h->Vp * 2);
+    rows = rows / 128 * 128;
+    if (rows < 128) rows = 128;
+    if (rows > NT) rows = round_up(NT, 128);
+    h->chunk_rows = (int)rows;
+    h->logits32 = b.take<float>(rows * h->Vp);
+    h->dlogits = b.take<__half>(rows * h->Vp);
+    // sampler (fp32 route)
+    h->samp_max = h->Nmax;
+    h->samp_ids = b.take<int32_t>(h->samp_max);
+    h->samp_out = b.take<int32_t>((int64_t)h->samp_max * 4096);
+    h->s_x = b.take<float>((int64_t)h->samp_max * wmax);
+    h->s_g = b.take<float>((int64_t)h->samp_max * h->G4);
+    h->s_logits = b.take<float>((int64_t)h->samp_max * h->V1);
+    h->s_c.resize(h->L);
+    h->s_h.resize(h->L);
+    for (int l = 0; l < h->L; ++l) {
+        h->s_c[l] = b.take<float>((int64_t)h->samp_max * h->H);
+        h->s_h[l] = b.take<float>((int64_t)h->samp_max * h->H);
+    }
+    tc_carve(h->tc, b, h->Nmax, h->T, h->V1, h->Vp, h->H, h->chunk_rows);
+    h->ws_need = round_up(b.off, 256);
+}
+
+// ---- GEMM dispatch: tcgen05 route unless the debug flag (or an unsupported shape) says SIMT -------
+static int gemm_f16(fsmg_handle* h, const GemmArgs& g, bool a_mn, bool b_mn, cudaStream_t s) {
+    if (g.M <= 0 || g.N <= 0) return FSMG_OK;
+    if (g.K <= 0) return FSMG_OK;
+    if (!(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) && tc_gemm_supported(g, a_mn, b_mn)) {
+        LAUNCH_COUNT(h);
+        return tc_gemm(h->tc, g, a_mn, b_mn, s);
+    }
+    launch_simt_gemm<__half, __half>(g, a_mn, b_mn, s);
+    LAUNCH_COUNT(h);
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+static GemmArgs mk(int M, int N, int K, const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                   float alpha = 1.0f, const float* bias = nullptr, int c_half = 0, int accumulate = 0, int atomic = 0) {
+    GemmArgs g;
+    g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.bias = bias; g.alpha = alpha; g.c_half = c_half; g.accumulate = accumulate; g.atomic = atomic;
+    return g;
+}
+
+static int refresh_weights(fsmg_handle* h, cudaStream_t s) {
+    const int TB = 256;
+    auto conv = [&](const float* in, int64_t ldi, __half* out, int64_t ldo, int rows, int cols) {
+        int64_t total = (int64_t)rows * ldo;
+        convert_f16_kernel<<<cdiv(total, TB), TB, 0, s>>>(in, ldi, out, ldo, rows, cols);
+        LAUNCH_COUNT(h);
+    };
+    auto tr = [&](const float* in, int64_t ldi, __half* out, int64_t ldo, int rows, int cols) {
+        dim3 grid(cdiv(cols, 32), cdiv(ldo, 32));
+        transpose_f16_kernel<<<grid, dim3(32, 8), 0, s>>>(in, ldi, out, ldo, rows, cols);
+        LAUNCH_COUNT(h);
+    };
+    conv(h->params + h->emb_off, h->E, h->emb16, h->Ep, h->V1, h->E);
+    for (auto& l : h->layers) {
+        const float* K = h->params + l.k_off;
+        conv(K, h->G4, l.K16, h->G4p, l.in + h->H, h->G4);
+        tr(K, h->G4, l.WxT16, l.inp, l.in, h->G4);                          // [in,4H] -> [4H, inp]
+        tr(K + (int64_t)l.in * h->G4, h->G4, l.WhT16, h->Hp, h->H, h->G4);  // [H,4H]  -> [4H, Hp]
+    }
+    conv(h->params + h->sw_off, h->V1, h->Ws16, h->Vp, h->H, h->V1);
+    tr(h->params + h->sw_off, h->V1, h->WsT16, h->Hp, h->H, h->V1);         // [H,V'] -> [V', Hp]
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+// ---- forward through the LSTM stack (embedding -> layers), stashing what BPTT needs -----------
+static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, cudaStream_t s) {
+    const int T = h->T, H = h->H, TB = 256;
+    const int64_t NT = (int64_t)N * T;
+    prep_tokens_kernel<<<cdiv(NT, TB), TB, 0, s>>>(d_tokens, h->x_ids, h->y_ids, N, T, h->V, h->V);
+    LAUNCH_COUNT(h);
+    {
+        int cols8 = h->Ep / 8;
+        gather_rows_f16_kernel<<<cdiv(NT * cols8, TB), TB, 0, s>>>(h->emb16, h->Ep, h->x_ids, h->xemb, h->Ep, NT, cols8);
+        LAUNCH_COUNT(h);
+    }
+    FSMG_LAUNCH_OK();
+    for (int li = 0; li < h->L; ++li) {
+        LayerBuf& l = h->layers[li];
+        const __half* in = li == 0 ? h->xemb : h->layers[li - 1].hs;
+        const float* bias = h->params + l.b_off;
+        // hoisted input contraction: pre[NT,4H] = in[NT,in] * Wx + b   (K3 in SURVEY §2.1)
+        int rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre, h->G4, 1.0f, bias), false, false, s);
+        if (rc) return rc;
+        if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
+            tc_recurrent_supported(h->tc, N, H)) {
+            rc = tc_lstm_forward(h->tc, h->pre, l.WhT16, l.gates, l.c, l.hs, N, T, H, h->Hp, h->G4p, s);
+            LAUNCH_COUNT(h);
+            if (rc) return rc;
+            continue;
+        }
+        for (int t = 0; t < T; ++t) {
+            float* G = h->pre + (int64_t)t * N * h->G4;
+            if (t > 0) {
+                rc = gemm_f16(h, mk(N, h->G4, H, l.hs + (int64_t)(t - 1) * N * h->Hp, h->Hp, l.WhT16, h->Hp, G, h->G4,
+                                    1.0f, nullptr, 0, /*accumulate=*/1), false, false, s);
+                if (rc) return rc;
+            }
+            lstm_pointwise_fwd_kernel<__half><<<cdiv((int64_t)N * H, TB), TB, 0, s>>>(
+                G, h->G4, t ? l.c + (int64_t)(t - 1) * N * H : nullptr, l.gates + (int64_t)t * N * h->G4p, h->G4p,
+                l.c + (int64_t)t * N * H, l.hs + (int64_t)t * N * h->Hp, h->Hp, N, H);
+            LAUNCH_COUNT(h);
+        }
+        FSMG_LAUNCH_OK();
+    }
+    return FSMG_OK;
+}
+
+// ---- projection + softmax/NLL (+ its backward when train) over L2-sized token chunks ------------
+static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float* d_nll_user, cudaStream_t s) {
+    const int T = h->T, H = h->H;
+    const int64_t NT = (int64_t)N * T;
+    const __half* hs = h->layers[h->L - 1].hs;
+    const float* sb = h->params + h->sb_off;
+    float* g_sw = h->grads ? h->grads + h->sw_off : nullptr;
+    float* g_sb = h->grads ? h->grads + h->sb_off : nullptr;
+    float* nll_out = d_nll_user ? d_nll_user : h->nll;
+    const bool use_tc = !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) && tc_projection_supported(h->tc, H, h->V1);
+    for (int64_t r0 = 0; r0 < NT; r0 += h->chunk_rows) {
+        int mc = (int)((NT - r0 < h->chunk_rows) ? NT - r0 : h->chunk_rows);
+        const __half* hc = hs + r0 * h->Hp;
+        int rc;
+        if (use_tc) {
+            // fused: logits tile -> online (max,sumexp) partials + target logit; fp16 logits only when training
+            rc = tc_projection_fwd(h->tc, hc, h->Hp, h->WsT16, h->Hp, sb, h->y_ids, r0, mc, N, T, H, h->V1,
+                                   train ? h->dlogits : nullptr, h->Vp, h->lse, nll_out, s);
+            h->launches += train ? 3 : 2;
+            if (rc) return rc;
+        } else {
+            rc = gemm_f16(h, mk(mc, h->V1, H, hc, h->Hp, h->WsT16, h->Hp, h->logits32, h->Vp, 1.0f, sb), false, false, s);
+            if (rc) return rc;
+            rowwise_nll_kernel<<<mc, 256, 0, s>>>(h->logits32, h->Vp, h->V1, h->y_ids, r0, N, T, h->lse, nll_out,
+                                                  train ? h->dlogits : nullptr, h->Vp);
+            LAUNCH_COUNT(h);
+            FSMG_LAUNCH_OK();
+        }
+        if (!train) continue;
+        // db_s += loss_scale * colsum(dlogits)
+        {
+            int rpb = 64;
+            dim3 grid(cdiv(h->V1, 128), cdiv(mc, rpb));
+            colsum_f16_kernel<<<grid, 128, 0, s>>>(h->dlogits, h->Vp, mc, h->V1, loss_scale, g_sb, rpb);
+            LAUNCH_COUNT(h);
+        }
+        // dH[chunk] = dlogits * Ws^T   (unscaled; fp32)
+        rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H), false, false, s);
+        if (rc) return rc;
+        // dWs += loss_scale * hs_chunk^T * dlogits   (contraction over the chunk's tokens)
+        rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, g_sw, h->V1, loss_scale, nullptr, 0, 1, 0), true, true, s);
+        if (rc) return rc;
+    }
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s) {
+    const int T = h->T, H = h->H, TB = 256;
+    const int64_t NT = (int64_t)N * T;
+    int cur = 0;  // dact[cur] holds dL/dh_t of the current layer ([NT,H] fp32)
+    for (int li = h->L - 1; li >= 0; --li) {
+        LayerBuf& l = h->layers[li];
+        const __half* in = li == 0 ? h->xemb : h->layers[li - 1].hs;
+        const __half* Wh_rows = l.K16 + (int64_t)l.in * h->G4p;  // kernel[in:, :] as [H, 4H] K-major
+        float* dh_all = h->dact[cur];
+        int rc;
+        bool persistent = !(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
+                          tc_recurrent_supported(h->tc, N, H);
+        if (persistent) {
+            rc = tc_lstm_backward(h->tc, dh_all, Wh_rows, l.gates, l.c, h->dgates, N, T, H, h->G4p, s);
+            LAUNCH_COUNT(h);
+            if (rc) return rc;
+        } else {
+            for (int t = T - 1; t >= 0; --t) {
+                if (t < T - 1) {
+                    rc = gemm_f16(h, mk(N, H, h->G4, h->dgates + (int64_t)(t + 1) * N * h->G4p, h->G4p, Wh_rows, h->G4p,
+                                        h->dh_rec, H), false, false, s);
+                    if (rc) return rc;
+                }
+                lstm_pointwise_bwd_kernel<<<cdiv((int64_t)N * H, TB), TB, 0, s>>>(
+                    dh_all + (int64_t)t * N * H, H, t < T - 1 ? h->dh_rec : nullptr, l.gates + (int64_t)t * N * h->G4p,
+                    h->G4p, l.c + (int64_t)t * N * H, t ? l.c + (int64_t)(t - 1) * N * H : nullptr, h->dc_next,
+                    h->dgates + (int64_t)t * N * h->G4p, h->G4p, N, H, t == T - 1);
+                LAUNCH_COUNT(h);
+            }
+            FSMG_LAUNCH_OK();
+        }
+        // db = loss_scale * colsum(dgates)
+        {
+            int rpb = 256;
+            dim3 grid(cdiv(h->G4, 128), cdiv(NT, rpb));
+            colsum_f16_kernel<<<grid, 128, 0, s>>>(h->dgates, h->G4p, NT, h->G4, loss_scale, h->grads + l.b_off, rpb);
+            LAUNCH_COUNT(h);
+        }
+        // dK[:in]  = loss_scale * in^T * dgates        (contraction over all tokens)
+        float* gK = h->grads + l.k_off;
+        rc = gemm_f16(h, mk(l.in, h->G4, (int)NT, in, l.inp, h->dgates, h->G4p, gK, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
+        if (rc) return rc;
+        // dK[in:]  = loss_scale * h_{t-1}^T * dgates_t  (tokens of steps 1..T-1; h_{-1} = 0)
+        if (T > 1) {
+            rc = gemm_f16(h, mk(H, h->G4, (int)(NT - N), l.hs, h->Hp, h->dgates + (int64_t)N * h->G4p, h->G4p,
+                                gK + (int64_t)l.in * h->G4, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
+            if (rc) return rc;
+        }
+        // dInput[NT,in] = dgates * kernel[:in,:]^T
+        float* dnext = h->dact[cur ^ 1];
+        rc = gemm_f16(h, mk((int)NT, l.in, h->G4, h->dgates, h->G4p, l.K16, h->G4p, dnext, l.in), false, false, s);
+        if (rc) return rc;
+        if (li == 0) {
+            scatter_emb_grad_kernel<<<(unsigned)NT, 128, 0, s>>>(dnext, l.in, h->x_ids, NT, h->E, loss_scale,
+                                                                 h->grads + h->emb_off, h->grads + h->n_params + 1);
+            LAUNCH_COUNT(h);
+        }
+        cur ^= 1;
+    }
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+static int check_call(fsmg_handle* h, int n_seqs) {
+    if (!h) return set_error(FSMG_ERR_INVALID, "null handle");
+    if (!h->bound) return set_error(FSMG_ERR_STATE, "fsmg_bind has not been called");
+    if (n_seqs <= 0 || n_seqs > h->Nmax)
+        return set_error(FSMG_ERR_CAPACITY, "n_seqs=%d outside [1, max_seqs=%d]", n_seqs, h->Nmax);
+    return FSMG_OK;
+}
+
+}  // namespace fsmg
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* fsmg_last_error(void) { return fsmg::last_error().c_str(); }
+int fsmg_abi_version(void) { return FSMG_ABI_VERSION; }
+
+int fsmg_create(const fsmg_config* cfg, const char* scope_name, fsmg_handle** out) {
+    if (!cfg || !out) return set_error(FSMG_ERR_INVALID, "null argument");
+    if (cfg->vocab <= 0 || cfg->embed <= 0 || cfg->hidden <= 0 || cfg->layers <= 0 || cfg->max_len <= 0 || cfg->max_seqs <= 0)
+        return set_error(FSMG_ERR_INVALID, "non-positive dimension in fsmg_config");
+    if (cfg->max_len > 4096) return set_error(FSMG_ERR_INVALID, "max_len > 4096 unsupported");
+    fsmg_handle* h = new fsmg_handle();
+    h->cfg = *cfg;
+    h->scope = scope_name && *scope_name ? scope_name : "lstm_baseline";
+    h->V = cfg->vocab; h->V1 = cfg->vocab + 1; h->E = cfg->embed; h->H = cfg->hidden; h->L = cfg->layers;
+    h->T = cfg->max_len; h->Nmax = cfg->max_seqs;
+    h->Ep = (int)round_up(h->E, 8); h->Hp = (int)round_up(h->H, 8); h->G4 = 4 * h->H; h->G4p = (int)round_up(h->G4, 8);
+    h->Vp = (int)round_up(h->V1, 8);
+    // flat parameter layout, TF get_vars() order (reference tf_model.py:99-104)
+    int64_t off = 0;
+    auto add = [&](const std::string& name, int rows, int cols) {
+        fsmg_param_info pi;
+        memset(&pi, 0, sizeof pi);
+        snprintf(pi.name, sizeof pi.name, "%s", name.c_str());
+        pi.offset = off; pi.rows = rows; pi.cols = cols;
+        h->infos.push_back(pi);
+        int64_t o = off;
+        off = round_up(off + (int64_t)rows * cols, 64);
+        return o;
+    };
+    h->emb_off = add(h->scope + "/embedding", h->V1, h->E);
+    h->dense_begin = off;
+    h->layers.resize(h->L);
+    for (int l = 0; l < h->L; ++l) {
+        LayerBuf& lb = h->layers[l];
+        lb.in = l == 0 ? h->E : h->H;
+        lb.inp = (int)round_up(lb.in, 8);
+        std::string base = h->scope + "/rnn/multi_rnn_cell/cell_" + std::to_string(l) + "/basic_lstm_cell";
+        lb.k_off = add(base + "/kernel", lb.in + h->H, h->G4);
+        lb.b_off = add(base + "/bias", h->G4, 1);
+    }
+    h->sw_off = add(h->scope + "/softmax_w", h->H, h->V1);
+    h->sb_off = add(h->scope + "/softmax_b", h->V1, 1);
+    h->n_params = off;
+    carve(h, nullptr);
+    *out = h;
+    return FSMG_OK;
+}
+
+void fsmg_destroy(fsmg_handle* h) {
+    if (!h) return;
+    if (h->h_tok) cudaFreeHost(h->h_tok);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    delete h;
+}
+
+int64_t fsmg_param_count(const fsmg_handle* h) { return h ? h->n_params : 0; }
+int64_t fsmg_grad_count(const fsmg_handle* h) { return h ? h->n_params + FSMG_GRAD_EXTRA : 0; }
+int64_t fsmg_workspace_bytes(const fsmg_handle* h) { return h ? h->ws_need : 0; }
+int fsmg_num_params(const fsmg_handle* h) { return h ? (int)h->infos.size() : 0; }
+int fsmg_param_info_at(const fsmg_handle* h, int index, fsmg_param_info* out) {
+    if (!h || !out || index < 0 || index >= (int)h->infos.size()) return set_error(FSMG_ERR_INVALID, "bad param index");
+    *out = h->infos[index];
+    return FSMG_OK;
+}
+int64_t fsmg_last_launch_count(const fsmg_handle* h) { return h ? h->launches : 0; }
+
+int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, float* d_adam_v, void* d_workspace,
+              int64_t workspace_bytes) {
+    if (!h || !d_params || !d_workspace) return set_error(FSMG_ERR_INVALID, "null argument");
+    if (workspace_bytes < h->ws_need)
+        return set_error(FSMG_ERR_CAPACITY, "workspace %lld < required %lld bytes", (long long)workspace_bytes, (long long)h->ws_need);
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255) || (reinterpret_cast<uintptr_t>(d_params) & 15))
+        return set_error(FSMG_ERR_INVALID, "workspace must be 256-byte aligned, params 16-byte aligned");
+    h->params = d_params; h->grads = d_grads; h->adam_m = d_adam_m; h->adam_v = d_adam_v;
+    h->ws = (char*)d_workspace; h->ws_bytes = workspace_bytes;
+    carve(h, h->ws);
+    int rc = tc_init(h->tc);
+    if (rc) return rc;
+    h->bound = true;
+    return FSMG_OK;
+}
+
+int fsmg_refresh_weights(fsmg_handle* h, void* stream) {
+    if (!h || !h->bound) return set_error(FSMG_ERR_STATE, "not bound");
+    return refresh_weights(h, (cudaStream_t)stream);
+}
+
+int fsmg_forward_nll(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, float* d_nll, float* d_sum_nll, void* stream) {
+    int rc = check_call(h, n_seqs);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    h->launches = 0;
+    rc = forward_lstm(h, d_tokens, n_seqs, s);
+    if (rc) return rc;
+    rc = projection(h, n_seqs, false, 0.0f, d_nll, s);
+    if (rc) return rc;
+    if (d_sum_nll) {
+        FSMG_CUDA_OK(cudaMemsetAsync(d_sum_nll, 0, sizeof(float), s));
+        sum_f32_kernel<<<148, 256, 0, s>>>(d_nll ? d_nll : h->nll, (int64_t)n_seqs * h->T, d_sum_nll);
+        LAUNCH_COUNT(h);
+        FSMG_LAUNCH_OK();
+    }
+    return FSMG_OK;
+}
+
+int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, float loss_scale, float* d_nll, void* stream) {
+    int rc = check_call(h, n_seqs);
+    if (rc) return rc;
+    if (!h->grads) return set_error(FSMG_ERR_STATE, "no gradient buffer bound");
+    cudaStream_t s = (cudaStream_t)stream;
+    h->launches = 0;
+    FSMG_CUDA_OK(cudaMemsetAsync(h->grads, 0, sizeof(float) * (h->n_params + FSMG_GRAD_EXTRA), s));
+    rc = forward_lstm(h, d_tokens, n_seqs, s);
+    if (rc) return rc;
+    rc = projection(h, n_seqs, true, loss_scale, d_nll, s);
+    if (rc) return rc;
+    sum_f32_kernel<<<148, 256, 0, s>>>(d_nll ? d_nll : h->nll, (int64_t)n_seqs * h->T, h->grads + h->n_params);
+    LAUNCH_COUNT(h);
+    rc = backward_lstm(h, n_seqs, loss_scale, s);
+    if (rc) return rc;
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+int fsmg_apply_update(fsmg_handle* h, int64_t step, float* d_out_norm, void* stream) {
+    if (!h || !h->bound) return set_error(FSMG_ERR_STATE, "not bound");
+    if (!h->grads || !h->adam_m || !h->adam_v) return set_error(FSMG_ERR_STATE, "optimizer buffers not bound");
+    cudaStream_t s = (cudaStream_t)stream;
+    // exponential_decay on the pre-increment step, fp32 like TF (A.8); Adam bias correction (A.7)
+    float lr_k = h->cfg.lr * powf(0.5f, (float)step / (float)h->cfg.n_decay);
+    double t = (double)step + 1.0;
+    double alpha = (double)lr_k * sqrt(1.0 - pow((double)h->cfg.beta2, t)) / (1.0 - pow((double)h->cfg.beta1, t));
+    float* dense_sq = h->scalars + 8;
+    FSMG_CUDA_OK(cudaMemsetAsync(dense_sq, 0, sizeof(float), s));
+    sqnorm_f32_kernel<<<296, 256, 0, s>>>(h->grads, h->dense_begin, h->n_params, dense_sq);
+    clip_adam_kernel<<<592, 256, 0, s>>>(h->params, h->grads, h->adam_m, h->adam_v, h->n_params, dense_sq,
+                                         h->grads + h->n_params + 1, h->cfg.max_grad_norm, (float)alpha, h->cfg.beta1,
+                                         h->cfg.beta2, h->cfg.eps, d_out_norm);
+    h->launches += 2;
+    FSMG_LAUNCH_OK();
+    return refresh_weights(h, s);
+}
+
+int fsmg_sample_greedy(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t* d_out, void* stream) {
+    if (!h || !h->bound) return set_error(FSMG_ERR_STATE, "not bound");
+    if (n_songs <= 0 || n_songs > h->samp_max) return set_error(FSMG_ERR_CAPACITY, "n_songs=%d outside [1,%d]", n_songs, h->samp_max);
+    if (n_tokens <= 0) return set_error(FSMG_ERR_INVALID, "n_tokens must be positive");
+    cudaStream_t s = (cudaStream_t)stream;
+    h->launches = 0;
+    const int H = h->H, TB = 256, n = n_songs;
+    if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && tc_sampler_supported(h->tc, n, H)) {
+        int rc = tc_sample_greedy(h->tc, n, n_tokens, d_out, s);
+        LAUNCH_COUNT(h);
+        return rc;
+    }
+    fill_i32_kernel<<<cdiv(n, TB), TB, 0, s>>>(h->samp_ids, n, h->V);  // word = start word (lstm_baseline.py:138)
+    LAUNCH_COUNT(h);
+    for (int l = 0; l < h->L; ++l) {  // zero_state (lstm_baseline.py:140)
+        FSMG_CUDA_OK(cudaMemsetAsync(h->s_c[l], 0, sizeof(float) * n * H, s));
+        FSMG_CUDA_OK(cudaMemsetAsync(h->s_h[l], 0, sizeof(float) * n * H, s));
+    }
+    for (int step = 0; step < n_tokens; ++step) {
+        gather_rows_f32_kernel<<<cdiv((int64_t)n * h->E, TB), TB, 0, s>>>(h->params + h->emb_off, h->E, h->samp_ids, h->s_x, h->E, n, h->E);
+        LAUNCH_COUNT(h);
+        const float* in = h->s_x;
+        int in_w = h->E;
+        for (int l = 0; l < h->L; ++l) {
+            LayerBuf& lb = h->layers[l];
+            const float* K = h->params + lb.k_off;
+            // fp32 weights, fp32 FMA: argmax near-ties need fp32-grade logits
+            launch_simt_gemm<float, float>(mk(n, h->G4, in_w, in, in_w, K, h->G4, h->s_g, h->G4, 1.0f, h->params + lb.b_off), false, true, s);
+            launch_simt_gemm<float, float>(mk(n, h->G4, H, h->s_h[l], H, K + (int64_t)in_w * h->G4, h->G4, h->s_g, h->G4, 1.0f, nullptr, 0, 1), false, true, s);
+            lstm_pointwise_fwd_kernel<float><<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, h->s_c[l], nullptr, 0, h->s_c[l], h->s_h[l], H, n, H);
+            h->launches += 3;
+            in = h->s_h[l];
+            in_w = H;
+        }
+        launch_simt_gemm<float, float>(mk(n, h->V1, H, in, H, h->params + h->sw_off, h->V1, h->s_logits, h->V1, 1.0f, h->params + h->sb_off), false, true, s);
+        argmax_rows_kernel<<<n, 256, 0, s>>>(h->s_logits, h->V1, h->V1, h->samp_ids, d_out, n_tokens, step);
+        h->launches += 2;
+    }
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------
+static int ensure_host_staging(fsmg_handle* h, int64_t tok_elems) {
+    if (!h->h_scal) FSMG_CUDA_OK(cudaHostAlloc((void**)&h->h_scal, 64 * sizeof(float), cudaHostAllocDefault));
+    if (tok_elems > h->h_tok_elems) {
+        if (h->h_tok) cudaFreeHost(h->h_tok);
+        h->h_tok = nullptr;
+        FSMG_CUDA_OK(cudaHostAlloc((void**)&h->h_tok, tok_elems * sizeof(int32_t), cudaHostAllocDefault));
+        h->h_tok_elems = tok_elems;
+    }
+    return FSMG_OK;
+}
+
+int fsmg_eval_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, float* h_mean_nll, float* h_nll, void* stream) {
+    int rc = check_call(h, n_seqs);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n = (int64_t)n_seqs * h->T;
+    rc = ensure_host_staging(h, (int64_t)h->Nmax * h->T);
+    if (rc) return rc;
+    memcpy(h->h_tok, h_tokens, n * sizeof(int32_t));
+    FSMG_CUDA_OK(cudaMemcpyAsync(h->tok_stage, h->h_tok, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    rc = fsmg_forward_nll(h, h->tok_stage, n_seqs, nullptr, h->scalars, s);
+    if (rc) return rc;
+    FSMG_CUDA_OK(cudaMemcpyAsync(h->h_scal, h->scalars, sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h_nll) FSMG_CUDA_OK(cudaMemcpyAsync(h_nll, h->nll, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    FSMG_CUDA_OK(cudaStreamSynchronize(s));
+    if (h_mean_nll) *h_mean_nll = (float)((double)h->h_scal[0] / ((double)n + 1e-12));
+    return FSMG_OK;
+}
+
+int fsmg_train_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, int64_t step, float* h_mean_loss, void* stream) {
+    int rc = check_call(h, n_seqs);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t n = (int64_t)n_seqs * h->T;
+    rc = ensure_host_staging(h, (int64_t)h->Nmax * h->T);
+    if (rc) return rc;
+    memcpy(h->h_tok, h_tokens, n * sizeof(int32_t));
+    FSMG_CUDA_OK(cudaMemcpyAsync(h->tok_stage, h->h_tok, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    float loss_scale = (float)(1.0 / ((double)n + 1e-12));
+    rc = fsmg_forward_backward(h, h->tok_stage, n_seqs, loss_scale, nullptr, s);
+    if (rc) return rc;
+    rc = fsmg_apply_update(h, step, nullptr, s);  // keeps accumulating h->launches
+    if (rc) return rc;
+    FSMG_CUDA_OK(cudaMemcpyAsync(h->h_scal, h->grads + h->n_params, sizeof(float), cudaMemcpyDeviceToHost, s));
+    FSMG_CUDA_OK(cudaStreamSynchronize(s));
+    if (h_mean_loss) *h_mean_loss = (float)((double)h->h_scal[0] / ((double)n + 1e-12));
+    return FSMG_OK;
+}
+
+int fsmg_sample_host(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t* h_out, void* stream) {
+    if (!h || !h->bound) return set_error(FSMG_ERR_STATE, "not bound");
+    if (n_tokens > 4096) return set_error(FSMG_ERR_CAPACITY, "n_tokens > 4096");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = fsmg_sample_greedy(h, n_songs, n_tokens, h->samp_out, s);
+    if (rc) return rc;
+    FSMG_CUDA_OK(cudaMemcpyAsync(h_out, h->samp_out, (int64_t)n_songs * n_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    FSMG_CUDA_OK(cudaStreamSynchronize(s));
+    return FSMG_OK;
+}
+
+int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const void* d_b_f16, float* d_c,
+                    int32_t a_mn_major, int32_t b_mn_major, int32_t use_simt, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t lda = a_mn_major ? m : k, ldb = b_mn_major ? n : k;
+    GemmArgs g = mk(m, n, k, d_a_f16, lda, d_b_f16, ldb, d_c, n);
+    if (use_simt) {
+        launch_simt_gemm<__half, __half>(g, a_mn_major != 0, b_mn_major != 0, s);
+        FSMG_LAUNCH_OK();
+        return FSMG_OK;
+    }
+    static fsmg::TcContext ctx;
+    int rc = tc_init(ctx);
+    if (rc) return rc;
+    if (!tc_gemm_supported(g, a_mn_major != 0, b_mn_major != 0)) return set_error(FSMG_ERR_INVALID, "shape unsupported by the tcgen05 GEMM");
+    return tc_gemm(ctx, g, a_mn_major != 0, b_mn_major != 0, s);
+}
+
+}  // extern "C"

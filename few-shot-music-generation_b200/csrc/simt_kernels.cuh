@@ -1,0 +1,403 @@
+// simt_kernels.cuh — CUDA-core kernels of libfsmg: the element-wise / gather / reduction stages
+// of the hot path (used by every route) and a generic fp32-accumulate SIMT GEMM that serves
+// (a) as the debug route for every contraction (FSMG_FLAG_SIMT_GEMM) and (b) as the fp32-exact
+// contraction of the greedy sampler, where argmax ties need fp32-grade logits.
+//
+// Reference semantics: src/models/lstm_baseline.py:38-87,135-156 and SURVEY.md Appendix A.
+#pragma once
+#include "common.cuh"
+
+namespace fsmg {
+
+// ============================================================================================
+// Generic SIMT GEMM:  C[m,n] (op)= alpha * sum_k A(m,k) * B(n,k) (+ bias[n])
+//   A is K-major (A[m*lda+k]) or MN-major (A[k*lda+m]); same for B (B[n*ldb+k] / B[k*ldb+n]).
+//   fp32 accumulation in a fixed k order.
+// ============================================================================================
+struct GemmArgs {
+    int M, N, K;
+    const void* A; int64_t lda;
+    const void* B; int64_t ldb;
+    void* C; int64_t ldc;
+    const float* bias;   // per-n, may be null
+    float alpha;
+    int c_half;          // 1: C is __half, 0: float
+    int accumulate;      // 1: C += (float C only, non-atomic read-modify-write)
+    int atomic;          // 1: atomicAdd into float C
+};
+
+__device__ __forceinline__ float ld_elem(const float* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ld_elem(const __half* p, int64_t i) { return __half2float(p[i]); }
+
+template <typename TA, typename TB, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(256) simt_gemm_kernel(GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const TA* A = reinterpret_cast<const TA*>(g.A);
+    const TB* B = reinterpret_cast<const TB*>(g.B);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            int i = tid + p * 256;
+            int mm, kk;
+            if (A_MN) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+            int gm = m0 + mm, gk = k0 + kk;
+            float v = 0.0f;
+            if (gm < g.M && gk < g.K) v = A_MN ? ld_elem(A, (int64_t)gk * g.lda + gm) : ld_elem(A, (int64_t)gm * g.lda + gk);
+            As[kk][mm] = v;
+            int nn;
+            if (B_MN) { nn = i & 63; kk = i >> 6; } else { kk = i & 15; nn = i >> 4; }
+            int gn = n0 + nn; gk = k0 + kk;
+            v = 0.0f;
+            if (gn < g.N && gk < g.K) v = B_MN ? ld_elem(B, (int64_t)gk * g.ldb + gn) : ld_elem(B, (int64_t)gn * g.ldb + gk);
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int gm = m0 + ty * 4 + i;
+        if (gm >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int gn = n0 + tx * 4 + j;
+            if (gn >= g.N) continue;
+            float v = g.alpha * acc[i][j];
+            if (g.bias) v += g.bias[gn];
+            int64_t idx = (int64_t)gm * g.ldc + gn;
+            if (g.c_half) {
+                reinterpret_cast<__half*>(g.C)[idx] = __float2half_rn(v);
+            } else {
+                float* c = reinterpret_cast<float*>(g.C);
+                if (g.atomic) atomicAdd(c + idx, v);
+                else if (g.accumulate) c[idx] += v;
+                else c[idx] = v;
+            }
+        }
+    }
+}
+
+template <typename TA, typename TB>
+static inline void launch_simt_gemm(const GemmArgs& g, bool a_mn, bool b_mn, cudaStream_t s) {
+    dim3 grid(cdiv(g.N, 64), cdiv(g.M, 64));
+    if (!a_mn && !b_mn) simt_gemm_kernel<TA, TB, false, false><<<grid, 256, 0, s>>>(g);
+    else if (a_mn && b_mn) simt_gemm_kernel<TA, TB, true, true><<<grid, 256, 0, s>>>(g);
+    else if (a_mn) simt_gemm_kernel<TA, TB, true, false><<<grid, 256, 0, s>>>(g);
+    else simt_gemm_kernel<TA, TB, false, true><<<grid, 256, 0, s>>>(g);
+}
+
+// ============================================================================================
+// Token preparation: convert_tokens_to_input_and_target (reference base_model.py:63-86) on the
+// device, re-ordered time-major: r = t*N + n.   x[r] = t ? tok[n,t-1] : V ;  y[r] = tok[n,t]
+// ============================================================================================
+__global__ void prep_tokens_kernel(const int32_t* __restrict__ tok, int32_t* __restrict__ x,
+                                   int32_t* __restrict__ y, int N, int T, int start_word, int vmax) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= (int64_t)N * T) return;
+    int t = (int)(r / N), n = (int)(r % N);
+    int cur = tok[(int64_t)n * T + t];
+    int prev = t ? tok[(int64_t)n * T + t - 1] : start_word;
+    // ids outside [0, V] would index out of the tables: clamp (the reference would raise in TF)
+    cur = min(max(cur, 0), vmax);
+    prev = min(max(prev, 0), vmax);
+    x[r] = prev;
+    y[r] = cur;
+}
+
+// embedding_lookup (lstm_baseline.py:41): out[r,:] = table16[ids[r],:]  (fp16 rows, 16-byte vectors)
+__global__ void gather_rows_f16_kernel(const __half* __restrict__ table, int64_t ld_table,
+                                       const int32_t* __restrict__ ids, __half* __restrict__ out,
+                                       int64_t ld_out, int64_t rows, int cols8) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = rows * cols8;
+    if (i >= total) return;
+    int64_t r = i / cols8;
+    int c = (int)(i % cols8);
+    const uint4* src = reinterpret_cast<const uint4*>(table + (int64_t)ids[r] * ld_table) + c;
+    reinterpret_cast<uint4*>(out + r * ld_out)[c] = __ldg(src);
+}
+
+// fp32 gather (sampler): out[r,:] = table[ids[r],:]
+__global__ void gather_rows_f32_kernel(const float* __restrict__ table, int64_t ld_table,
+                                       const int32_t* __restrict__ ids, float* __restrict__ out,
+                                       int64_t ld_out, int rows, int cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * cols) return;
+    int r = (int)(i / cols), c = (int)(i % cols);
+    out[(int64_t)r * ld_out + c] = table[(int64_t)ids[r] * ld_table + c];
+}
+
+// ============================================================================================
+// BasicLSTMCell element-wise stage ([TF-lib] A.2): gates i,j,f,o ; forget_bias 1
+//   c = c_prev*sigmoid(f+1) + sigmoid(i)*tanh(j) ; h = tanh(c)*sigmoid(o)
+// G: pre-activations fp32 [N, ldg] (columns [i|j|f|o], each H wide).
+// ============================================================================================
+template <typename TH>
+__global__ void lstm_pointwise_fwd_kernel(const float* __restrict__ G, int64_t ldg,
+                                          const float* __restrict__ c_prev,   // [N,H] or null (zeros)
+                                          __half* __restrict__ gates_out, int64_t ldgo,  // may be null
+                                          float* __restrict__ c_out,          // [N,H]
+                                          TH* __restrict__ h_out, int64_t ldh, int N, int H) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * H) return;
+    int n = (int)(idx / H), u = (int)(idx % H);
+    const float* g = G + (int64_t)n * ldg;
+    float i_ = sigmoidf_(g[u]);
+    float j_ = tanhf_(g[H + u]);
+    float f_ = sigmoidf_(g[2 * H + u] + 1.0f);
+    float o_ = sigmoidf_(g[3 * H + u]);
+    float cp = c_prev ? c_prev[(int64_t)n * H + u] : 0.0f;
+    float c = cp * f_ + i_ * j_;
+    float h = tanhf_(c) * o_;
+    c_out[(int64_t)n * H + u] = c;
+    if (sizeof(TH) == 2) reinterpret_cast<__half*>(h_out)[(int64_t)n * ldh + u] = __float2half_rn(h);
+    else reinterpret_cast<float*>(h_out)[(int64_t)n * ldh + u] = h;
+    if (gates_out) {
+        __half* go = gates_out + (int64_t)n * ldgo;
+        go[u] = __float2half_rn(i_);
+        go[H + u] = __float2half_rn(j_);
+        go[2 * H + u] = __float2half_rn(f_);
+        go[3 * H + u] = __float2half_rn(o_);
+    }
+}
+
+// Reverse-time cell backward for one step t (what tf.gradients derives for A.2):
+//   dh = dh_out[t] + dh_rec ; do = dh*tanh(c) ; dc = dh*o*(1-tanh(c)^2) + dc_next
+//   dgi = dc*j*i(1-i) ; dgj = dc*i*(1-j^2) ; dgf = dc*c_prev*f(1-f) ; dgo = do*o(1-o) ; dc_next' = dc*f
+// Activations are "unscaled" (loss = sum nll); the 1/(N*T) factor is applied in the weight-grad epilogues.
+__global__ void lstm_pointwise_bwd_kernel(const float* __restrict__ dh_out, int64_t ld_dho,  // [N,H] block t
+                                          const float* __restrict__ dh_rec,                  // [N,H] or null
+                                          const __half* __restrict__ gates, int64_t ldg,      // block t
+                                          const float* __restrict__ c, const float* __restrict__ c_prev,  // block t, t-1 (null -> 0)
+                                          float* __restrict__ dc_next,                        // [N,H] in/out
+                                          __half* __restrict__ dgates, int64_t lddg, int N, int H, int first) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)N * H) return;
+    int n = (int)(idx / H), u = (int)(idx % H);
+    const __half* g = gates + (int64_t)n * ldg;
+    float i_ = __half2float(g[u]), j_ = __half2float(g[H + u]);
+    float f_ = __half2float(g[2 * H + u]), o_ = __half2float(g[3 * H + u]);
+    float dh = dh_out[(int64_t)n * ld_dho + u] + (dh_rec ? dh_rec[(int64_t)n * H + u] : 0.0f);
+    float tc = tanhf_(c[(int64_t)n * H + u]);
+    float cp = c_prev ? c_prev[(int64_t)n * H + u] : 0.0f;
+    float dcn = first ? 0.0f : dc_next[(int64_t)n * H + u];
+    float d_o = dh * tc;
+    float dc = dh * o_ * (1.0f - tc * tc) + dcn;
+    __half* dg = dgates + (int64_t)n * lddg;
+    dg[u] = __float2half_rn(dc * j_ * i_ * (1.0f - i_));
+    dg[H + u] = __float2half_rn(dc * i_ * (1.0f - j_ * j_));
+    dg[2 * H + u] = __float2half_rn(dc * cp * f_ * (1.0f - f_));
+    dg[3 * H + u] = __float2half_rn(d_o * o_ * (1.0f - o_));
+    dc_next[(int64_t)n * H + u] = dc * f_;
+}
+
+// ============================================================================================
+// Row-wise softmax / NLL over materialised fp32 logits (SIMT route): one CTA per token row.
+//   lse = logsumexp(logits[r,:V']) ; nll = lse - logits[r,y]   ([TF-lib] A.5, natural log)
+//   if dlogits: dlogits[r,v] = exp(logit-lse) - [v==y]   (unscaled, fp16)
+// nll is written sequence-major: nll_out[n*T + t] with r = t*N + n (row0 = global row of chunk row 0).
+// ============================================================================================
+__global__ void rowwise_nll_kernel(const float* __restrict__ logits, int64_t ld, int vp1,
+                                   const int32_t* __restrict__ y, int64_t row0, int N, int T,
+                                   float* __restrict__ lse_out, float* __restrict__ nll_out,
+                                   __half* __restrict__ dlogits, int64_t ldd) {
+    __shared__ float red[32];
+    int64_t lr = blockIdx.x;          // row inside the chunk
+    int64_t r = row0 + lr;            // global time-major row
+    const float* row = logits + lr * ld;
+    float m = -INFINITY;
+    for (int v = threadIdx.x; v < vp1; v += blockDim.x) m = fmaxf(m, row[v]);
+    m = block_max(m, red);
+    float s = 0.0f;
+    for (int v = threadIdx.x; v < vp1; v += blockDim.x) s += expf(row[v] - m);
+    s = block_sum(s, red);
+    float lse = m + logf(s);
+    int tgt = y[r];
+    if (threadIdx.x == 0) {
+        if (lse_out) lse_out[r] = lse;
+        int t = (int)(r / N), n = (int)(r % N);
+        if (nll_out) nll_out[(int64_t)n * T + t] = lse - row[tgt];
+    }
+    if (dlogits) {
+        __half* d = dlogits + lr * ldd;
+        for (int v = threadIdx.x; v < vp1; v += blockDim.x) {
+            float p = expf(row[v] - lse) - (v == tgt ? 1.0f : 0.0f);
+            d[v] = __float2half_rn(p);
+        }
+        for (int64_t v = vp1 + threadIdx.x; v < ldd; v += blockDim.x) d[v] = __float2half_rn(0.0f);
+    }
+}
+
+// Column sums of an fp16 matrix [rows, cols] (ld) scaled by alpha, atomically added to out[cols]:
+// bias gradients (db = sum_r dgates[r,:], db_s = sum_r dlogits[r,:]).
+__global__ void colsum_f16_kernel(const __half* __restrict__ X, int64_t ld, int64_t rows, int cols,
+                                  float alpha, float* __restrict__ out, int rows_per_block) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    int64_t r1 = min(rows, r0 + rows_per_block);
+    if (c >= cols) return;
+    float s = 0.0f;
+    for (int64_t r = r0; r < r1; ++r) s += __half2float(X[r * ld + c]);
+    atomicAdd(out + c, alpha * s);
+}
+
+// Embedding gradient: IndexedSlices(values = dX[r,:], indices = x[r]) densified by scatter-add,
+// plus the per-occurrence square norm TF's clip_by_global_norm sees ([TF-lib] A.6).
+__global__ void scatter_emb_grad_kernel(const float* __restrict__ dX, int64_t ld, const int32_t* __restrict__ x,
+                                        int64_t rows, int E, float alpha, float* __restrict__ gemb,
+                                        float* __restrict__ occ_sq) {
+    __shared__ float red[32];
+    int64_t r = blockIdx.x;
+    float sq = 0.0f;
+    if (r < rows) {
+        const float* src = dX + r * ld;
+        float* dst = gemb + (int64_t)x[r] * E;
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            float v = alpha * src[e];
+            atomicAdd(dst + e, v);
+            sq += v * v;
+        }
+    }
+    sq = block_sum(sq, red);
+    if (threadIdx.x == 0) atomicAdd(occ_sq, sq);
+}
+
+// sum of a float array -> atomicAdd into out (grid-stride)
+__global__ void sum_f32_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// sum of squares over [begin, end) of a float array -> atomicAdd (double accumulation per thread)
+__global__ void sqnorm_f32_kernel(const float* __restrict__ x, int64_t begin, int64_t end, float* __restrict__ out) {
+    __shared__ float red[32];
+    float s = 0.0f;
+    for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x) {
+        float v = x[i];
+        s = fmaf(v, v, s);
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ============================================================================================
+// clip_by_global_norm + TF-Adam ([TF-lib] A.6, A.7) over the flat buffers.
+//   scalars[0] = dense square norm (all trainables except the embedding), scalars[1] = occ square norm
+//   scale = clip / max(norm, clip) ; m,v update ; theta -= alpha_t * m / (sqrt(v) + eps)
+// alpha_t (lr schedule + bias correction, A.7/A.8) is computed on the host in fp32/double.
+// ============================================================================================
+__global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, int64_t n, const float* __restrict__ dense_sq,
+                                 const float* __restrict__ occ_sq, float clip, float alpha_t, float beta1,
+                                 float beta2, float eps, float* __restrict__ norm_out) {
+    float norm = sqrtf(*dense_sq + *occ_sq);
+    float scale = clip / fmaxf(norm, clip);
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * scale;
+        float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = p[i] - alpha_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+// fp32 master -> fp16 operand copies.  out[r*ldo + c] = in[r*ldi + c]  (row-major copy, pad cols zeroed)
+__global__ void convert_f16_kernel(const float* __restrict__ in, int64_t ldi, __half* __restrict__ out, int64_t ldo,
+                                   int rows, int cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * ldo) return;
+    int r = (int)(i / ldo), c = (int)(i % ldo);
+    out[i] = __float2half_rn(c < cols ? in[(int64_t)r * ldi + c] : 0.0f);
+}
+// out[c*ldo + r] = in[r*ldi + c]  for r in [0,rows), c in [0,cols)   (32x32 smem transpose)
+__global__ void transpose_f16_kernel(const float* __restrict__ in, int64_t ldi, __half* __restrict__ out, int64_t ldo,
+                                     int rows, int cols) {
+    __shared__ float tile[32][33];
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int r = r0 + j, c = c0 + threadIdx.x;
+        tile[j][threadIdx.x] = (r < rows && c < cols) ? in[(int64_t)r * ldi + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int c = c0 + j, r = r0 + threadIdx.x;
+        if (c < cols && r < ldo) out[(int64_t)c * ldo + r] = __float2half_rn(r < rows ? tile[threadIdx.x][j] : 0.0f);
+    }
+}
+
+// ============================================================================================
+// Greedy decode helpers (lstm_baseline.py:152-153): first-index argmax per row of fp32 logits.
+// ============================================================================================
+__global__ void argmax_rows_kernel(const float* __restrict__ logits, int64_t ld, int cols,
+                                   int32_t* __restrict__ next_ids, int32_t* __restrict__ out, int64_t out_stride,
+                                   int64_t out_off) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    int r = blockIdx.x;
+    const float* row = logits + (int64_t)r * ld;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float v = row[c];
+        if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sv[w] = best; si[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        best = lane < nw ? sv[lane] : -INFINITY;
+        bi = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            next_ids[r] = bi;
+            out[(int64_t)r * out_stride + out_off] = bi;
+        }
+    }
+}
+
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+}  // namespace fsmg

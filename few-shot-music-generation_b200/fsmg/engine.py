@@ -1,0 +1,217 @@
+"""Host-side engine: owns the PyTorch tensors (parameters, Adam slots, flat gradient buffer,
+workspace) and drives libfsmg.so through its C-ABI.  PyTorch is plumbing here (device memory,
+streams, torch.distributed); all arithmetic of the hot path runs in the CUDA library.
+
+Replaces the TensorFlow session of the reference (src/models/tf_model.py:80-97 and the
+sess.run calls of src/models/lstm_baseline.py:104,125,150).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import FsmgError, fsmg_config, fsmg_param_info
+
+
+def glorot_uniform_init(shapes: Dict[str, tuple], seed: int) -> Dict[str, np.ndarray]:
+    """TF-1.x default initialiser for get_variable (glorot_uniform): every
+    trainable U(-l, l), l = sqrt(6/(fan_in+fan_out)) — including softmax_b, with fan_in =
+    fan_out = len for vectors — except the LSTM bias, which BasicLSTMCell zero-initialises.
+    TF's RNG stream cannot be reproduced, so only the distribution matches
+    (reference tf_model.py:81 seeds with config['seed'])."""
+    rng = np.random.RandomState(seed)
+    out = {}
+    for name, shape in shapes.items():
+        if name.endswith("/bias"):
+            out[name] = np.zeros(shape, np.float32)
+            continue
+        fan_in, fan_out = (shape[0], shape[0]) if len(shape) == 1 else shape
+        limit = math.sqrt(6.0 / (fan_in + fan_out))
+        out[name] = rng.uniform(-limit, limit, size=shape).astype(np.float32)
+    return out
+
+
+class Engine:
+    """One engine per process/GPU.  `config` uses the reference's keys (lstm_baseline.py:21-29)."""
+
+    def __init__(self, config: dict, max_seqs: int, device: Optional[torch.device] = None, flags: int = 0,
+                 process_group=None):
+        if not torch.cuda.is_available():
+            raise FsmgError("fsmg requires a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        self.config = dict(config)
+        self.V = int(config["input_size"])
+        self.E = int(config["embedding_size"])
+        self.H = int(config["hidden_size"])
+        self.L = int(config.get("n_layers", 1))
+        self.T = int(config["max_len"])
+        self.max_seqs = int(max_seqs)
+        self.scope = str(config.get("name", "lstm_baseline"))
+        flags |= int(os.environ.get("FSMG_FLAGS", "0"))
+        cfg = fsmg_config(
+            vocab=self.V, embed=self.E, hidden=self.H, layers=self.L, max_len=self.T, max_seqs=self.max_seqs,
+            n_decay=int(config.get("n_decay", 10000)), flags=flags, lr=float(config.get("lr", 5e-3)),
+            max_grad_norm=float(config.get("max_grad_norm", 5)), beta1=0.9, beta2=0.999, eps=1e-8, reserved=0.0)
+        self.flags = flags
+        h = C.c_void_p()
+        _lib.check(self.lib.fsmg_create(C.byref(cfg), self.scope.encode(), C.byref(h)))
+        self.h = h
+        self.n_params = int(self.lib.fsmg_param_count(h))
+        self.n_grads = int(self.lib.fsmg_grad_count(h))
+        ws_bytes = int(self.lib.fsmg_workspace_bytes(h))
+        dev = self.device
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.n_grads, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.adam_v = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.workspace = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+        ws_ptr = (self.workspace.data_ptr() + 255) // 256 * 256
+        _lib.check(self.lib.fsmg_bind(h, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                      self.adam_v.data_ptr(), ws_ptr, ws_bytes))
+        self.infos: List[dict] = []
+        for i in range(self.lib.fsmg_num_params(h)):
+            pi = fsmg_param_info()
+            _lib.check(self.lib.fsmg_param_info_at(h, i, C.byref(pi)))
+            shape = (pi.rows, pi.cols) if pi.cols > 1 or not pi.name.decode().endswith(("/bias", "/softmax_b")) else (pi.rows,)
+            self.infos.append(dict(name=pi.name.decode(), offset=int(pi.offset), shape=shape))
+        self.global_step = 0
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        self._nll = torch.empty(self.max_seqs * self.T, dtype=torch.float32, device=dev)
+        self._sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._tok = torch.empty(self.max_seqs * self.T, dtype=torch.int32, device=dev)
+        self._pinned_tok = torch.empty(self.max_seqs * self.T, dtype=torch.int32).pin_memory()
+        self._pinned_scal = torch.empty(8, dtype=torch.float32).pin_memory()
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def param_shapes(self) -> Dict[str, tuple]:
+        return {i["name"]: tuple(i["shape"]) for i in self.infos}
+
+    def _view(self, flat: torch.Tensor, info: dict) -> torch.Tensor:
+        n = int(np.prod(info["shape"]))
+        return flat[info["offset"]: info["offset"] + n].view(*info["shape"])
+
+    def param_views(self, which: str = "params") -> Dict[str, torch.Tensor]:
+        flat = {"params": self.params, "grads": self.grads, "adam_m": self.adam_m, "adam_v": self.adam_v}[which]
+        return {i["name"]: self._view(flat, i) for i in self.infos}
+
+    def load_params(self, params: Dict[str, np.ndarray], strict: bool = True) -> List[str]:
+        """Inject weights by TF variable name (name AND shape must match, like
+        optimistic_restore, reference tf_model.py:28-75).  Returns the names loaded."""
+        loaded = []
+        views = self.param_views()
+        for name, view in views.items():
+            if name not in params:
+                if strict:
+                    raise KeyError(name)
+                continue
+            arr = np.asarray(params[name], dtype=np.float32)
+            if tuple(arr.shape) != tuple(view.shape):
+                if strict:
+                    raise ValueError(f"{name}: shape {arr.shape} != {tuple(view.shape)}")
+                continue
+            view.copy_(torch.from_numpy(arr))
+            loaded.append(name)
+        self.refresh_weights()
+        return loaded
+
+    def init_params(self, seed: int) -> None:
+        self.load_params(glorot_uniform_init(self.param_shapes(), seed))
+
+    def export(self, which: str = "params") -> Dict[str, np.ndarray]:
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.param_views(which).items()}
+
+    def refresh_weights(self) -> None:
+        _lib.check(self.lib.fsmg_refresh_weights(self.h, self._stream()))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- device-resident entry points ---------------------------------------------------------------
+    def forward_nll(self, tokens: torch.Tensor):
+        """tokens int32 [N,T] on the device -> (per-token nll [N,T] fp32, sum nll [1])."""
+        n = int(tokens.shape[0])
+        assert tokens.dtype == torch.int32 and tokens.is_cuda and tokens.is_contiguous() and tokens.shape[1] == self.T
+        nll = self._nll[: n * self.T]
+        _lib.check(self.lib.fsmg_forward_nll(self.h, tokens.data_ptr(), n, nll.data_ptr(), self._sum.data_ptr(), self._stream()))
+        return nll.view(n, self.T), self._sum
+
+    def forward_backward(self, tokens: torch.Tensor, global_tokens: Optional[int] = None) -> None:
+        n = int(tokens.shape[0])
+        assert tokens.dtype == torch.int32 and tokens.is_cuda and tokens.is_contiguous() and tokens.shape[1] == self.T
+        gt = global_tokens if global_tokens is not None else n * self.T * self.world
+        loss_scale = float(1.0 / (float(gt) + 1e-12))
+        _lib.check(self.lib.fsmg_forward_backward(self.h, tokens.data_ptr(), n, loss_scale, 0, self._stream()))
+
+    def train_step_device(self, tokens: torch.Tensor, global_tokens: Optional[int] = None) -> torch.Tensor:
+        """One optimizer step on device-resident tokens.  Data parallel: every rank passes its
+        shard; ONE all-reduce (sum) of the flat gradient buffer — which also carries sum(nll)
+        and the per-occurrence embedding-gradient square norm — then clip+Adam on every rank.
+        Returns a 1-element device tensor holding the mean loss of the global batch."""
+        n = int(tokens.shape[0])
+        gt = global_tokens if global_tokens is not None else n * self.T * self.world
+        self.forward_backward(tokens, gt)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+        _lib.check(self.lib.fsmg_apply_update(self.h, self.global_step, 0, self._stream()))
+        self.global_step += 1
+        return self.grads[self.n_params: self.n_params + 1] / (float(gt) + 1e-12)
+
+    def sample_greedy_device(self, n_songs: int, n_tokens: int) -> torch.Tensor:
+        out = torch.empty((n_songs, n_tokens), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.fsmg_sample_greedy(self.h, n_songs, n_tokens, out.data_ptr(), self._stream()))
+        return out
+
+    # ---- host-buffer entry points (numpy in, python scalars out: what LSTMBaseline uses) -------------
+    def _stage(self, tokens: np.ndarray) -> torch.Tensor:
+        tok = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1, self.T)
+        n = tok.shape[0]
+        if n > self.max_seqs:
+            raise FsmgError(f"{n} sequences > engine capacity {self.max_seqs}")
+        self._pinned_tok[: n * self.T].copy_(torch.from_numpy(tok.reshape(-1)))
+        dev = self._tok[: n * self.T]
+        dev.copy_(self._pinned_tok[: n * self.T], non_blocking=True)
+        return dev.view(n, self.T)
+
+    def train_host(self, tokens: np.ndarray, global_tokens: Optional[int] = None) -> float:
+        loss = self.train_step_device(self._stage(tokens), global_tokens)
+        self._pinned_scal[:1].copy_(loss, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._pinned_scal[0])
+
+    def eval_host(self, tokens: np.ndarray, return_nll: bool = False):
+        dev = self._stage(tokens)
+        nll, s = self.forward_nll(dev)
+        n_tok = dev.numel()
+        self._pinned_scal[:1].copy_(s, non_blocking=True)
+        out = nll.cpu().numpy().copy() if return_nll else None
+        torch.cuda.current_stream(self.device).synchronize()
+        mean = float(self._pinned_scal[0]) / (float(n_tok) + 1e-12)
+        return (mean, out) if return_nll else mean
+
+    def sample_host(self, n_songs: int, n_tokens: int) -> np.ndarray:
+        return self.sample_greedy_device(n_songs, n_tokens).cpu().numpy()
+
+    def last_launch_count(self) -> int:
+        return int(self.lib.fsmg_last_launch_count(self.h))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.fsmg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,140 @@
+"""Episodic support/query sampler with the reference's API
+(reference src/data/episode.py:15-18 `Episode`, :44-80 `EpisodeSampler`, :82-149
+`load_sampler_from_config`), re-implemented for two kinds of corpora that need none of the
+reference's absent dependencies (nltk / pretty_midi):
+
+* ``synthetic_lyrics`` / ``synthetic_midi`` — seeded token streams generated in memory;
+* ``lyrics`` / ``midi`` — a directory tree ``root/<artist>/<song>.<max_len>.npy`` holding the
+  token caches the reference's loaders persist (reference src/data/base_loader.py:52-64),
+  so a corpus tokenised once by the reference can be trained on directly.
+
+The RNG call sequence matches the reference on old NumPy: ``choice(n, size, replace=False)`` over
+artists, then per artist ``choice(n_songs, S+Q, replace=False)`` with the first Q drawn songs
+forming the query set (reference :34-41, :62-74).
+"""
+import os
+
+import numpy as np
+import yaml
+from numpy.random import RandomState
+
+MIDI_VOCAB = 16 * 128 * 2 + 32 * 16 + 100  # 4708 event ids (reference src/data/midi_loader.py:53-60)
+
+
+class Episode(object):
+    def __init__(self, support, query):
+        self.support = support
+        self.query = query
+
+
+class TokenCorpus(object):
+    """artists -> list of int32 [max_len] songs, zero-padded (pad id 0 is a real token)."""
+
+    def __init__(self, songs_by_artist, vocab, max_len):
+        self.artists = list(songs_by_artist)
+        self.vocab = int(vocab)
+        self.max_len = int(max_len)
+
+    def __len__(self):
+        return len(self.artists)
+
+
+def _zipf_tokens(rng, shape, vocab):
+    pmf = 1.0 / np.arange(1, vocab + 1, dtype=np.float64)
+    cdf = np.cumsum(pmf / pmf.sum())
+    return np.minimum(np.searchsorted(cdf, rng.random_sample(size=shape)), vocab - 1).astype(np.int32)
+
+
+def make_synthetic_corpus(kind, max_len, vocab, n_artists, songs_per_artist, seed, split):
+    rng = RandomState((int(seed) * 7919 + {'train': 0, 'val': 1, 'test': 2}.get(split, 3)) % (2 ** 31))
+    shape = (n_artists, songs_per_artist, max_len)
+    if kind == 'synthetic_lyrics':
+        tok = _zipf_tokens(rng, shape, vocab)
+    else:
+        tok = rng.randint(0, vocab, size=shape).astype(np.int32)
+    return TokenCorpus([tok[a] for a in range(n_artists)], vocab, max_len)
+
+
+def load_npy_corpus(root, max_len, min_songs, split, props=(8, 1, 1), seed=0):
+    suffix = '.%s.npy' % max_len
+    artists = []
+    vocab = 0
+    for artist in sorted(os.listdir(root)):
+        adir = os.path.join(root, artist)
+        if not os.path.isdir(adir):
+            continue
+        songs = [np.load(os.path.join(adir, f)).astype(np.int32) for f in sorted(os.listdir(adir)) if f.endswith(suffix)]
+        if len(songs) >= min_songs:
+            artists.append(np.stack(songs))
+            vocab = max(vocab, int(max(s.max() for s in songs)) + 1)
+    if not artists:
+        raise RuntimeError('no artist under %s has >= %d token caches "*%s" (tokenise the corpus with the '
+                           "reference's loaders first: nltk / pretty_midi are not available here)" % (root, min_songs, suffix))
+    order = RandomState(seed).permutation(len(artists))
+    total = float(sum(props))
+    n_train = int(round(len(artists) * props[0] / total))
+    n_val = int(round(len(artists) * props[1] / total))
+    pick = {'train': order[:n_train], 'val': order[n_train:n_train + n_val], 'test': order[n_train + n_val:]}[split]
+    return TokenCorpus([artists[i] for i in pick], vocab, max_len)
+
+
+class EpisodeSampler(object):
+    def __init__(self, dataset, batch_size, support_size, query_size, max_len, dtype=np.int32, seed=None):
+        self.dataset = dataset
+        self.batch_size = batch_size
+        self.support_size = support_size
+        self.query_size = query_size
+        self.max_len = max_len
+        self.dtype = dtype
+        self.random = RandomState(seed) if seed is not None else np.random
+
+    def get_episode(self):
+        b, s, q = self.batch_size, self.support_size, self.query_size
+        support = np.zeros((b, s, self.max_len), dtype=self.dtype)
+        query = np.zeros((b, q, self.max_len), dtype=self.dtype)
+        artists = self.random.choice(len(self.dataset), size=b, replace=False)
+        for bi, ai in enumerate(artists):
+            songs = self.dataset.artists[ai]
+            pick = self.random.choice(len(songs), size=s + q, replace=False)
+            query[bi] = songs[pick[:q]]
+            support[bi] = songs[pick[q:]]
+        return Episode(support, query)
+
+    def get_num_unique_words(self):
+        return self.dataset.vocab
+
+    def detokenize(self, numpy_data):
+        # no lyrics/MIDI decoder without nltk/pretty_midi: a space-separated id string (write_seq's str branch)
+        return ' '.join(str(int(t)) for t in np.asarray(numpy_data).reshape(-1))
+
+
+def load_sampler_from_config(config):
+    """Create an EpisodeSampler from a config dict / yaml path (reference :82-149)."""
+    if isinstance(config, str):
+        config = yaml.safe_load(open(config, 'r'))
+    elif not isinstance(config, dict):
+        config = yaml.safe_load(config)
+    for key in ('dataset_path', 'query_size', 'support_size', 'batch_size', 'max_len', 'dataset', 'split'):
+        if key not in config:
+            raise RuntimeError('required config key "%s" not found' % key)
+    min_songs = config['support_size'] + config['query_size']
+    kind = config['dataset']
+    if kind in ('synthetic_lyrics', 'synthetic_midi'):
+        vocab = int(config.get('synthetic_vocab', 10000 if kind == 'synthetic_lyrics' else MIDI_VOCAB))
+        corpus = make_synthetic_corpus(kind, config['max_len'], vocab, int(config.get('synthetic_artists', 64)),
+                                       max(int(config.get('synthetic_songs_per_artist', 24)), min_songs),
+                                       config.get('dataset_seed', 0), config['split'])
+    elif kind in ('lyrics', 'midi'):
+        root = config['dataset_path']
+        if not os.path.isdir(root):
+            raise RuntimeError('required data directory %s does not exist' % root)
+        props = (config.get('train_proportion', 8), config.get('val_proportion', 1), config.get('test_proportion', 1))
+        corpus = load_npy_corpus(root, config['max_len'], min_songs, config['split'], props, config.get('dataset_seed', 0))
+        if kind == 'midi':
+            corpus.vocab = MIDI_VOCAB
+    else:
+        raise RuntimeError('unknown dataset "%s"' % kind)
+    if len(corpus) < config['batch_size']:
+        raise RuntimeError('split "%s" has %d artists < batch_size %d' % (config['split'], len(corpus), config['batch_size']))
+    return EpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
+                          config['max_len'], seed=config.get('seed', None))

@@ -1,0 +1,150 @@
+/*
+ * fsmg.h — C-ABI of libfsmg.so, the B200 (sm_100a) engine for the episodic LSTM baseline of
+ * AI-ON/Few-Shot-Music-Generation.
+ *
+ * The reference has no native boundary: its model/compute boundary is
+ *     feed_dict -> tf.Session.run        (reference src/models/lstm_baseline.py:98-105,120-125,144-151)
+ * inside models.lstm_baseline.LSTMBaseline.{train,eval,sample}.  Every entry point below
+ * replaces one use of that boundary and cites it.  The Python class
+ * `models.lstm_baseline.LSTMBaseline` (few-shot-music-generation_b200/src/models/lstm_baseline.py)
+ * binds these symbols with ctypes; see INTEGRATION.md for the stub a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is a DEVICE pointer owned by the caller
+ *     (PyTorch tensors), every pointer named h_* is a HOST pointer owned by the caller;
+ *   - the library allocates no device memory: parameters, Adam slots, gradients and the
+ *     workspace are bound once with fsmg_bind();
+ *   - all device work is enqueued on the cudaStream_t passed as `stream` (a void*; NULL = the
+ *     legacy default stream); calls are asynchronous unless stated otherwise;
+ *   - return value: 0 = FSMG_OK, negative = error (fsmg_last_error() gives the text); nothing
+ *     throws across the ABI;
+ *   - one handle per device; a handle is not thread-safe.
+ *
+ * Token layout: `tokens` is int32 [n_seqs, T] row-major, exactly the arrays
+ * EpisodeSampler.get_episode() yields after flatten_first_two_dims
+ * (reference src/models/base_model.py:57-60, src/data/episode.py:62-74).  The start-word shift of
+ * convert_tokens_to_input_and_target (base_model.py:63-86) happens on the device.
+ */
+#ifndef FSMG_H_
+#define FSMG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSMG_ABI_VERSION 1
+
+enum {
+    FSMG_OK = 0,
+    FSMG_ERR_INVALID = -1,   /* bad argument / config */
+    FSMG_ERR_CUDA = -2,      /* a CUDA runtime / driver call failed */
+    FSMG_ERR_STATE = -3,     /* call order (e.g. not bound) */
+    FSMG_ERR_CAPACITY = -4   /* n_seqs / workspace larger than what was bound */
+};
+
+/* flags for fsmg_config.flags */
+enum {
+    FSMG_FLAG_SIMT_GEMM = 1,     /* debug: route every contraction through the fp32-accumulate SIMT GEMM
+                                    instead of the tcgen05 kernels (same data flow and dtypes) */
+    FSMG_FLAG_SIMT_RECURRENT = 2 /* debug: per-step launches instead of the persistent recurrent kernel */
+};
+
+/* Hyper-parameters read by the reference model:
+ *   lstm_baseline.py:21-29 (input_size, max_len, embedding_size, hidden_size, n_layers, lr,
+ *   max_grad_norm), :77-81 (n_decay); Adam defaults of tf.train.AdamOptimizer (:82). */
+typedef struct fsmg_config {
+    int32_t vocab;         /* config['input_size'] = V; start word = V; V' = V + 1 */
+    int32_t embed;         /* embedding_size E */
+    int32_t hidden;        /* hidden_size H */
+    int32_t layers;        /* n_layers */
+    int32_t max_len;       /* max_len T (time steps of the unrolled graph) */
+    int32_t max_seqs;      /* capacity: sequences per call (B*(S+Q) * episodes_per_step) */
+    int32_t n_decay;       /* exponential_decay steps */
+    int32_t flags;         /* FSMG_FLAG_* */
+    float lr;              /* base learning rate */
+    float max_grad_norm;   /* clip_by_global_norm threshold */
+    float beta1, beta2, eps; /* Adam (0.9, 0.999, 1e-8 in the reference) */
+    float reserved;
+} fsmg_config;
+
+typedef struct fsmg_handle fsmg_handle;
+
+/* One trainable tensor inside the flat fp32 parameter buffer, in the order
+ * TFModel.get_vars() returns them (reference src/models/tf_model.py:99-104):
+ * embedding, cell_l/kernel, cell_l/bias ..., softmax_w, softmax_b. */
+typedef struct fsmg_param_info {
+    char name[96];     /* TF variable name, e.g. "lstm_baseline/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/kernel" */
+    int64_t offset;    /* element offset into the flat buffer */
+    int32_t rows, cols;/* cols = 1 for vectors */
+} fsmg_param_info;
+
+const char* fsmg_last_error(void);
+int fsmg_abi_version(void);
+
+/* Host-only construction (replaces TFModel.__init__ graph building, tf_model.py:80-97). */
+int fsmg_create(const fsmg_config* cfg, const char* scope_name, fsmg_handle** out);
+void fsmg_destroy(fsmg_handle* h);
+
+/* Sizes the caller must allocate: flat parameter count (padded), gradient buffer count
+ * (= params + FSMG_GRAD_EXTRA scalar slots), workspace bytes. */
+#define FSMG_GRAD_EXTRA 8  /* [0]=sum of per-token NLL, [1]=per-occurrence embedding-grad square norm (TF clip quirk) */
+int64_t fsmg_param_count(const fsmg_handle* h);
+int64_t fsmg_grad_count(const fsmg_handle* h);
+int64_t fsmg_workspace_bytes(const fsmg_handle* h);
+int fsmg_num_params(const fsmg_handle* h);
+int fsmg_param_info_at(const fsmg_handle* h, int index, fsmg_param_info* out);
+
+/* Bind caller-owned device buffers (all fp32 except the opaque workspace).  Builds TMA
+ * descriptors.  d_params/d_adam_m/d_adam_v: fsmg_param_count() floats; d_grads: fsmg_grad_count(). */
+int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, float* d_adam_v,
+              void* d_workspace, int64_t workspace_bytes);
+
+/* Re-derive the fp16 operand copies of the weights from the fp32 master parameters.  Must be
+ * called after the caller writes d_params directly (init / checkpoint restore); fsmg_apply_update
+ * does it itself. */
+int fsmg_refresh_weights(fsmg_handle* h, void* stream);
+
+/* Forward + per-token NLL — LSTMBaseline.eval's sess.run(self._avg_neg_log)
+ * (lstm_baseline.py:115-125) and the loss half of train (:104).
+ *   d_tokens [n_seqs,T] int32; d_nll [n_seqs,T] fp32 (may be NULL);
+ *   d_sum_nll: 1 float, receives sum over tokens (mean = sum / (n_seqs*T + 1e-12), A.5). */
+int fsmg_forward_nll(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs,
+                     float* d_nll, float* d_sum_nll, void* stream);
+
+/* Forward + backward (tf.gradients, lstm_baseline.py:83-84) into d_grads: dense gradients of
+ * sum(nll) * loss_scale for every trainable, plus the two scalars of FSMG_GRAD_EXTRA.
+ * loss_scale = 1/(global token count + 1e-12): for data-parallel shards the caller passes the
+ * GLOBAL count, all-reduces d_grads (sum) and then calls fsmg_apply_update on every rank. */
+int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs,
+                          float loss_scale, float* d_nll, void* stream);
+
+/* clip_by_global_norm + Adam + exponential_decay + global_step++ (lstm_baseline.py:77-87) on the
+ * (already reduced) d_grads; refreshes the fp16 operand copies.  `step` = global_step before
+ * this update.  d_out_norm (1 float, may be NULL) receives the global norm. */
+int fsmg_apply_update(fsmg_handle* h, int64_t step, float* d_out_norm, void* stream);
+
+/* Greedy autoregressive decode fully on the device — LSTMBaseline.sample's python loop
+ * (lstm_baseline.py:135-156) for n_songs independent songs at once: start word V, zero state,
+ * argmax with first-index tie-break.  d_out [n_songs, n_tokens] int32. */
+int fsmg_sample_greedy(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t* d_out, void* stream);
+
+/* Host-buffer convenience entry points (what a ctypes/cgo caller with numpy/host arrays binds):
+ * pinned staging + H2D of tokens, the step, D2H of the result, stream-synchronised on return. */
+int fsmg_eval_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, float* h_mean_nll, float* h_nll, void* stream);
+int fsmg_train_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, int64_t step, float* h_mean_loss, void* stream);
+int fsmg_sample_host(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t* h_out, void* stream);
+
+/* Introspection for benchmarks/tests: number of kernel launches issued by the last call,
+ * and a GEMM self-test entry (C[M,N] = A[M,K] * B[N,K]^T, fp16 in, fp32 out) that drives the
+ * tcgen05 core directly. */
+int64_t fsmg_last_launch_count(const fsmg_handle* h);
+int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const void* d_b_f16,
+                    float* d_c, int32_t a_mn_major, int32_t b_mn_major, int32_t use_simt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSMG_H_ */

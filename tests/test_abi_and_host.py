@@ -1,0 +1,212 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/fsmg.h declares (no compute
+calls without a GPU), the host-only parts of the ABI work, and the host logic (sampler, config
+merge, plugin registry plumbing, data-parallel protocol over gloo) behaves like the reference."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import yaml
+
+ROOT = Path(__file__).resolve().parents[1]
+PKG = ROOT / "few-shot-music-generation_b200"
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    header = (ROOT / "include" / "fsmg.h").read_text()
+    declared = set(re.findall(r"\b(fsmg_[a-z_]+)\s*\(", header))
+    declared -= {"fsmg_config", "fsmg_handle", "fsmg_param_info"}
+    assert len(declared) >= 20
+    lib = C.CDLL(str(built_lib))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in fsmg.h but not exported"
+    from fsmg import _lib
+    assert set(_lib.SYMBOLS) == declared
+    assert _lib.load().fsmg_abi_version() == 1
+
+
+def test_host_only_abi_param_layout(built_lib):
+    from fsmg import _lib
+    lib = _lib.load()
+    cfg = _lib.fsmg_config(vocab=333, embed=50, hidden=36, layers=2, max_len=9, max_seqs=45, n_decay=10000, flags=0,
+                           lr=5e-3, max_grad_norm=5.0, beta1=0.9, beta2=0.999, eps=1e-8, reserved=0)
+    h = C.c_void_p()
+    assert lib.fsmg_create(C.byref(cfg), b"lstm_baseline", C.byref(h)) == 0
+    names, end = [], 0
+    for i in range(lib.fsmg_num_params(h)):
+        pi = _lib.fsmg_param_info()
+        assert lib.fsmg_param_info_at(h, i, C.byref(pi)) == 0
+        names.append((pi.name.decode(), pi.rows, pi.cols))
+        assert pi.offset >= end and pi.offset % 64 == 0
+        end = pi.offset + pi.rows * pi.cols
+    # TF get_vars() order and shapes
+    assert names == [
+        ("lstm_baseline/embedding", 334, 50),
+        ("lstm_baseline/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/kernel", 86, 144),
+        ("lstm_baseline/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/bias", 144, 1),
+        ("lstm_baseline/rnn/multi_rnn_cell/cell_1/basic_lstm_cell/kernel", 72, 144),
+        ("lstm_baseline/rnn/multi_rnn_cell/cell_1/basic_lstm_cell/bias", 144, 1),
+        ("lstm_baseline/softmax_w", 36, 334),
+        ("lstm_baseline/softmax_b", 334, 1),
+    ]
+    assert lib.fsmg_param_count(h) >= end and lib.fsmg_grad_count(h) == lib.fsmg_param_count(h) + 8
+    assert lib.fsmg_workspace_bytes(h) > 0
+    # error behaviour: calls before bind fail with a message instead of crashing
+    assert lib.fsmg_refresh_weights(h, None) != 0 and b"bound" in lib.fsmg_last_error()
+    bad = _lib.fsmg_config(vocab=0, embed=1, hidden=1, layers=1, max_len=1, max_seqs=1)
+    h2 = C.c_void_p()
+    assert lib.fsmg_create(C.byref(bad), b"x", C.byref(h2)) != 0
+    lib.fsmg_destroy(h)
+
+
+def test_engine_refuses_to_run_without_cuda(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fsmg import FsmgError
+    from fsmg.engine import Engine
+    with pytest.raises(FsmgError):
+        Engine(dict(input_size=10, embedding_size=8, hidden_size=8, n_layers=1, max_len=4), max_seqs=4)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from fsmg import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.FsmgError):
+        _lib.load()
+
+
+def test_product_path_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing shipped under the package may import or exec it."""
+    files = list((PKG / "fsmg").glob("*.py")) + list((PKG / "src").rglob("*.py")) + list((PKG / "csrc").glob("*"))
+    assert len(files) > 8
+    for path in files:
+        text = path.read_text(errors="ignore")
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), path
+        assert "oracle/" not in text and "lstm_oracle" not in text and "torch_ref" not in text, path
+
+
+def _merged_config(data, task, model):
+    cfgdir = PKG / "src" / "config"
+    cfg = yaml.safe_load(open(cfgdir / data))
+    cfg.update(yaml.safe_load(open(cfgdir / task)))
+    cfg.update(yaml.safe_load(open(cfgdir / model)))
+    return cfg
+
+
+def test_config_merge_keeps_reference_keys():
+    cfg = _merged_config("lyrics.yaml", "5shot.yaml", "lstm_baseline.yaml")
+    for key in ("name", "model_module_name", "model_class_name", "n_train", "n_decay", "print_every_n", "val_every_n",
+                "n_val", "n_test", "n_samples", "lr", "max_grad_norm", "batch_size", "embedding_size", "n_layers",
+                "hidden_size", "query_size", "support_size", "seed", "dataset", "dataset_path", "splits", "max_len"):
+        assert key in cfg, key
+    assert (cfg["embedding_size"], cfg["hidden_size"], cfg["batch_size"], cfg["max_len"]) == (250, 200, 5, 50)
+    assert (cfg["support_size"], cfg["query_size"], cfg["seed"]) == (5, 4, 1234)
+    assert cfg["model_module_name"] == "models.lstm_baseline" and cfg["model_class_name"] == "LSTMBaseline"
+    b200 = _merged_config("synthetic_lyrics.yaml", "5shot.yaml", "lstm_baseline_b200_lyrics.yaml")
+    assert (b200["hidden_size"], b200["embedding_size"], b200["max_len"], b200["episodes_per_step"]) == (512, 512, 128, 32)
+
+
+def test_episode_sampler_shapes_determinism_and_disjointness():
+    from data.episode import load_sampler_from_config
+    cfg = _merged_config("synthetic_lyrics_small.yaml", "5shot.yaml", "lstm_baseline_cpu_ref.yaml")
+    cfg["split"] = "train"
+    s1, s2 = load_sampler_from_config(cfg), load_sampler_from_config(cfg)
+    e1, e2 = s1.get_episode(), s2.get_episode()
+    assert e1.support.shape == (5, 5, 32) and e1.query.shape == (5, 4, 32) and e1.support.dtype == np.int32
+    np.testing.assert_array_equal(e1.support, e2.support)
+    np.testing.assert_array_equal(e1.query, e2.query)
+    assert s1.get_num_unique_words() == 10000 and e1.support.max() < 10000
+    # support and query songs of one artist are drawn without replacement
+    for b in range(5):
+        rows = np.concatenate([e1.support[b], e1.query[b]])
+        assert len({r.tobytes() for r in rows}) == 9
+    with pytest.raises(RuntimeError):
+        load_sampler_from_config({k: v for k, v in cfg.items() if k != "max_len"})
+
+
+def test_npy_corpus_reads_reference_token_caches(tmp_path):
+    from data.episode import load_sampler_from_config
+    rng = np.random.RandomState(0)
+    for a in range(12):
+        d = tmp_path / f"artist{a}"
+        d.mkdir()
+        for s in range(10):
+            np.save(d / f"song{s}.txt.16.npy", rng.randint(0, 99, size=16).astype(np.int32))
+    cfg = dict(dataset="lyrics", dataset_path=str(tmp_path), max_len=16, split="train", batch_size=5, support_size=5,
+               query_size=4, seed=1)
+    ep = load_sampler_from_config(cfg).get_episode()
+    assert ep.support.shape == (5, 5, 16) and ep.query.shape == (5, 4, 16)
+
+
+def test_base_model_token_helpers_match_reference_semantics():
+    from models.base_model import BaseModel, convert_tokens_to_input_and_target
+    tok = np.arange(24).reshape(2, 3, 4)
+    x, y = convert_tokens_to_input_and_target(tok, start_word=99)
+    assert x.shape == (6, 4) and (x[:, 0] == 99).all() and (x[:, 1:] == tok.reshape(6, 4)[:, :-1]).all()
+    assert (y == tok.reshape(6, 4)).all()
+    x, y = convert_tokens_to_input_and_target(tok)
+    assert x.shape == (6, 3) and (y == tok.reshape(6, 4)[:, 1:]).all()
+    with pytest.raises(NotImplementedError):
+        BaseModel({"name": "m"}).train(None)
+
+
+def test_train_cli_parses_reference_flags():
+    sys.path.insert(0, str(PKG / "src"))
+    from train.train import build_parser
+    a = build_parser().parse_args(["--data", "d.yaml", "--model", "m.yaml", "--task", "t.yaml", "--checkpt_dir", "c", "--init_dir", "i"])
+    assert (a.data, a.model, a.task, a.checkpt_dir, a.init_dir) == ("d.yaml", "m.yaml", "t.yaml", "c", "i")
+
+
+DP_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FSMG_ROOT"])
+from oracle import lstm_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"], rank=int(os.environ["RANK"]), world_size=2)
+cfg = dict(name="lstm_baseline", input_size=40, embedding_size=7, hidden_size=6, n_layers=1, max_len=5, lr=5e-3, n_decay=10000, max_grad_norm=0.05)
+params = O.glorot_init(cfg, 9, np.float64)
+tok = O.synthetic_tokens(np.random.RandomState(3), (8, 5), 40, "uniform")
+rank = dist.get_rank()
+shard = tok[rank * 4:(rank + 1) * 4]
+state = O.TrainState(params, cfg, np.float64)
+names = sorted(params)
+for step in range(3):
+    x, y = O.shift_inputs(shard, 40)
+    nll, _, cache = O.forward(state.params, x, y, np.float64, keep_cache=True)
+    grads, occ = O.backward(state.params, cache, np.float64, loss_denominator=tok.size)
+    # the engine's protocol: ONE all-reduce of [flat grads | sum nll | occ sqnorm]
+    flat = torch.from_numpy(np.concatenate([grads[k].reshape(-1) for k in names] + [np.array([nll.sum(), occ])]))
+    dist.all_reduce(flat)
+    flat = flat.numpy(); off = 0; red = {}
+    for k in names:
+        n = grads[k].size; red[k] = flat[off:off + n].reshape(grads[k].shape); off += n
+    O.apply_clip_adam(state, red, float(flat[-1]))
+if rank == 0:
+    single = O.TrainState(params, cfg, np.float64)
+    for step in range(3):
+        loss = O.train_step(single, tok)
+    for k in names:
+        np.testing.assert_allclose(state.params[k], single.params[k], rtol=1e-9, atol=1e-13)
+    print("DP_OK")
+dist.barrier()
+'''
+
+
+def test_data_parallel_protocol_world2_gloo(tmp_path):
+    """world_size-2 gloo run of the engine's DP protocol (flat grads + 2 scalars, one all-reduce,
+    redundant clip+Adam) with the oracle standing in for the kernels: equals the 1-process step."""
+    script = tmp_path / "dp_worker.py"
+    script.write_text(DP_WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=port, FSMG_ROOT=str(ROOT), OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "DP_OK" in outs[0]

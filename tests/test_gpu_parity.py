@@ -1,0 +1,239 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI
+(fsmg.Engine -> libfsmg.so) and through the reference-facing plugin class
+(models.lstm_baseline.LSTMBaseline), against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-token NLL within 1e-3 relative; greedy token indices
+bit-exact (wherever the fp64 oracle's own top-2 margin is not a numerical tie, < 1e-6);
+10-step training-loss trajectory within 1e-3.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import lstm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NLL_RTOL = 1e-3
+TIE_MARGIN = 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch_cuda(built_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch
+
+
+def make_engine(cfg, max_seqs, flags=0):
+    from fsmg.engine import Engine
+    return Engine(cfg, max_seqs=max_seqs, device="cuda:0", flags=flags)
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)))
+
+
+ROUTES = [pytest.param(3, id="simt"), pytest.param(0, id="tcgen05")]
+
+
+@pytest.mark.parametrize("flags", ROUTES)
+@pytest.mark.parametrize("case", ["tiny_l1", "tiny_l2", "odd_dims", "cfg1_cpu_ref"])
+def test_golden_nll_and_training_trajectory(torch_cuda, case, flags):
+    cfg, g = load_golden(case)
+    tokens = g["tokens"]
+    eng = make_engine(cfg, tokens.shape[1], flags)
+    eng.load_params(O.glorot_init(cfg, 1234))
+    mean, nll = eng.eval_host(tokens[0], return_nll=True)
+    assert rel_err(nll, g["nll_initial"]) < NLL_RTOL
+    assert abs(mean - g["nll_initial"].mean()) < 1e-3 * g["nll_initial"].mean()
+    losses = [eng.train_host(tokens[i]) for i in range(tokens.shape[0])]
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-3)
+    _, nll2 = eng.eval_host(tokens[0], return_nll=True)
+    assert rel_err(nll2, g["nll_after_training"]) < 2e-3  # 10 Adam steps of accumulated fp32/fp16 rounding
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", ROUTES)
+def test_gradients_clip_norm_and_adam_state_match_oracle(torch_cuda, flags):
+    cfg = dict(name="lstm_baseline", input_size=120, embedding_size=24, hidden_size=32, n_layers=2, max_len=7,
+               lr=5e-3, n_decay=10000, max_grad_norm=0.25)
+    params = O.glorot_init(cfg, 11)
+    rng = np.random.RandomState(5)
+    tok = O.synthetic_tokens(rng, (19, 7), 120, "zipf")  # repeated ids -> the A.6 occurrence-norm quirk matters
+    eng = make_engine(cfg, 19, flags)
+    eng.load_params(params)
+    dev = eng._stage(tok)
+    eng.forward_backward(dev, tok.size)
+    x, y = O.shift_inputs(tok, 120)
+    nll, loss, cache = O.forward(params, x, y, np.float64, keep_cache=True)
+    grads, occ = O.backward(params, cache, np.float64)
+    got = eng.export("grads")
+    for k, ref in grads.items():
+        scale = np.abs(ref).max()
+        assert np.abs(got[k] - ref).max() < 2e-3 * scale + 1e-9, k
+    extra = eng.grads[eng.n_params:].cpu().numpy()
+    assert abs(extra[0] - nll.sum()) < 1e-3 * nll.sum()
+    assert abs(extra[1] - occ) < 5e-3 * occ
+    # one update: parameters and Adam slots follow TF-Adam with the clip active
+    state = O.TrainState(params, cfg, np.float64)
+    norm = O.apply_clip_adam(state, grads, occ)
+    assert norm > cfg["max_grad_norm"]
+    import torch
+    norm_dev = torch.zeros(1, device="cuda:0")
+    from fsmg import _lib
+    _lib.check(eng.lib.fsmg_apply_update(eng.h, 0, norm_dev.data_ptr(), eng._stream()))
+    assert abs(float(norm_dev) - norm) < 3e-3 * norm
+    newp = eng.export("params")
+    for k in grads:
+        # first Adam step moves every element by ~alpha*sign(g): compare the update, not the value
+        du, dr = newp[k] - params[k], state.params[k] - params[k].astype(np.float64)
+        mask = np.abs(grads[k]) > 1e-3 * np.abs(grads[k]).max()
+        assert np.abs(du - dr)[mask].max() < 0.02 * np.abs(dr).max() + 1e-9, k
+    eng.close()
+
+
+@pytest.mark.parametrize("flags", ROUTES)
+def test_padded_and_single_sequence_inputs(torch_cuda, flags):
+    cfg = dict(name="lstm_baseline", input_size=64, embedding_size=16, hidden_size=16, n_layers=1, max_len=8)
+    params = O.glorot_init(cfg, 2)
+    eng = make_engine(cfg, 45, flags)
+    eng.load_params(params)
+    for tok in (np.zeros((1, 8), np.int32),                      # one all-padding sequence (pad id 0 is scored)
+                np.full((3, 8), 63, np.int32),                    # maximum id
+                O.synthetic_episode(np.random.RandomState(1), 5, 5, 4, 8, 64, "uniform", 0.5)[0].reshape(-1, 8)):
+        _, nll = eng.eval_host(tok, return_nll=True)
+        assert rel_err(nll, O.per_token_nll(params, tok, 64, np.float64)) < NLL_RTOL
+    eng.close()
+
+
+def test_capacity_and_argument_errors(torch_cuda):
+    from fsmg import FsmgError
+    cfg = dict(name="lstm_baseline", input_size=64, embedding_size=16, hidden_size=16, n_layers=1, max_len=8)
+    eng = make_engine(cfg, 4)
+    eng.init_params(0)
+    with pytest.raises(FsmgError):
+        eng.eval_host(np.zeros((5, 8), np.int32))
+    with pytest.raises(FsmgError):
+        eng.sample_host(5, 3)
+    eng.close()
+
+
+@pytest.mark.parametrize("case", ["tiny_l1", "tiny_l2", "odd_dims", "cfg1_cpu_ref"])
+def test_greedy_sampling_token_indices_bit_exact(torch_cuda, case):
+    cfg, g = load_golden(case)
+    eng = make_engine(cfg, 8)
+    eng.load_params(O.glorot_init(cfg, 1234))
+    n = len(g["sample"])
+    got = eng.sample_host(3, n)
+    assert (got[0] == got[1]).all() and (got[0] == got[2]).all()  # songs are independent and identical
+    want, margins = g["sample"].tolist(), g["sample_margins"]
+    for i in range(n):
+        if got[0, i] != want[i]:
+            assert margins[i] < TIE_MARGIN, f"token {i}: {got[0, i]} != {want[i]} with margin {margins[i]:.3e}"
+            break  # after a numerical tie the continuations legitimately differ
+    else:
+        return
+    assert i > 0
+
+
+def test_sampling_long_sequence_matches_fp32_oracle(torch_cuda):
+    cfg = dict(name="lstm_baseline", input_size=4708, embedding_size=96, hidden_size=128, n_layers=1, max_len=16)
+    params = O.glorot_init(cfg, 77)
+    eng = make_engine(cfg, 4)
+    eng.load_params(params)
+    got = eng.sample_host(2, 96)[0].tolist()
+    want, margins = O.sample_greedy(params, 96, np.float64, True)
+    for i, (a, b) in enumerate(zip(got, want)):
+        if a != b:
+            assert margins[i] < TIE_MARGIN, (i, a, b, margins[i])
+            break
+
+
+def _plugin_config(tmpdir=None, **over):
+    cfg = dict(name="lstm_baseline", model_module_name="models.lstm_baseline", model_class_name="LSTMBaseline",
+               input_size=200, embedding_size=32, hidden_size=32, n_layers=1, max_len=12, lr=5e-3, n_decay=10000,
+               max_grad_norm=5, batch_size=5, support_size=5, query_size=4, seed=1234, tensorboard=False)
+    cfg.update(over)
+    if tmpdir is not None:
+        cfg["checkpt_dir"] = str(tmpdir)
+    return cfg
+
+
+class _Ep:
+    def __init__(self, s, q):
+        self.support, self.query = s, q
+
+
+def test_plugin_class_train_eval_sample_like_the_reference(torch_cuda, tmp_path):
+    """Through the reference's registry: import_module(model_module_name).<class>(config)."""
+    from train.train import load_model_from_config
+    cfg = _plugin_config()
+    model = load_model_from_config(cfg)
+    assert model.name == "lstm_baseline"
+    params = O.glorot_init(cfg, 99)
+    model.set_params(params)
+    rng = np.random.RandomState(0)
+    ep = _Ep(*O.synthetic_episode(rng, 5, 5, 4, 12, 200))
+    # eval = query set only (reference lstm_baseline.py:115-118)
+    assert abs(model.eval(ep) - O.eval_episode(params, ep.query, 200)) < 1e-3 * 5.3
+    # train = support rows then query rows, one optimizer step, returns the pre-update loss
+    state = O.TrainState(params, cfg, np.float64)
+    for _ in range(3):
+        want = O.train_step(state, O.episode_train_tokens(ep.support, ep.query))
+        got = model.train(ep)
+        assert isinstance(got, float) and abs(got - want) < 1e-3 * want
+    assert model.global_step == 3
+    s = model.sample(ep.support[0], 12)
+    assert isinstance(s, list) and len(s) == 12 and all(isinstance(w, int) and 0 <= w <= 200 for w in s)
+    # a list of episodes = episodes_per_step
+    big = load_model_from_config(_plugin_config(episodes_per_step=2))
+    big.set_params(params)
+    ep2 = _Ep(*O.synthetic_episode(rng, 5, 5, 4, 12, 200))
+    toks = np.concatenate([O.episode_train_tokens(e.support, e.query) for e in (ep, ep2)])
+    assert abs(big.train([ep, ep2]) - O.train_step(O.TrainState(params, cfg, np.float64), toks)) < 1e-2
+
+
+def test_checkpoint_save_recover_roundtrip(torch_cuda, tmp_path):
+    from train.train import load_model_from_config
+    cfg = _plugin_config(tmp_path)
+    rng = np.random.RandomState(0)
+    ep = _Ep(*O.synthetic_episode(rng, 5, 5, 4, 12, 200))
+    a = load_model_from_config(cfg)
+    a.recover_or_init("")
+    for _ in range(2):
+        a.train(ep)
+    path = a.save(str(tmp_path))
+    assert path.endswith(os.path.join("lstm_baseline", "lstm_baseline-2.npz"))
+    b = load_model_from_config(cfg)
+    b.recover_or_init(str(tmp_path))
+    assert b.global_step == 2
+    for k, v in a.get_params().items():
+        np.testing.assert_array_equal(v, b.get_params()[k])
+    assert a.train(ep) == b.train(ep)  # Adam slots and step restored: the next step is identical
+    # a missing directory falls back to random init (recover_or_init semantics)
+    c = load_model_from_config(cfg)
+    c.recover_or_init(str(tmp_path / "nowhere"))
+    assert c.global_step == 0
+
+
+def test_train_entry_point_end_to_end(torch_cuda, tmp_path):
+    """`python -um train.train --data --model --task --checkpt_dir` on synthetic data (tiny schedule)."""
+    import subprocess
+    import sys
+    import yaml
+    from conftest import PKG
+    model_yaml = tmp_path / "model.yaml"
+    cfg = yaml.safe_load(open(PKG / "src" / "config" / "lstm_baseline_cpu_ref.yaml"))
+    cfg.update(n_train=6, print_every_n=3, val_every_n=3, n_val=2, n_test=2, n_samples=1, hidden_size=32, embedding_size=32)
+    yaml.safe_dump(cfg, open(model_yaml, "w"))
+    out = subprocess.run([sys.executable, "-um", "train.train", "--data", "config/synthetic_lyrics_small.yaml", "--model",
+                          str(model_yaml), "--task", "config/5shot.yaml", "--checkpt_dir", str(tmp_path / "ck")],
+                         cwd=str(PKG / "src"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Iter: 6, val-nll" in out.stdout and "Test Avg NLL" in out.stdout
+    assert (tmp_path / "ck" / "lstm_baseline" / "lstm_baseline-6.npz").exists()
+    assert (tmp_path / "ck" / "samples" / "sample_0" / "model_sample.txt").exists()
