@@ -116,13 +116,25 @@ def cpu_reference_steps(w: dict, steps: int, warmup: int, episodes: int):
     import torch
     from oracle import lstm_oracle as O
     from oracle.torch_ref import TorchRef
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     cfg = model_config(w)
     ref = TorchRef(O.glorot_init(cfg, 1234), cfg, torch.float32)
     wl = dict(w, episodes=episodes)
     batches = synthetic_batches(wl, steps + warmup, 1234)
     toks = [np.concatenate([O.episode_train_tokens(s, q) for s, q in b]) for b in batches]
+    # give the CPU path its best thread count: the tiny per-step matmuls of an LSTM get SLOWER with
+    # 100+ threads, so probe a few counts (one step each) and keep the fastest
+    avail = os.cpu_count() or 1
+    best, cores = None, 1
+    for th in sorted({min(avail, c) for c in (8, 16, 32, avail)}):
+        torch.set_num_threads(th)
+        t0 = time.perf_counter()
+        ref.train_step(toks[0])
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, th
+        if dt > 8.0:   # bounded: do not keep probing configurations that are already slow
+            break
+    torch.set_num_threads(cores)
     for i in range(warmup):
         ref.train_step(toks[i])
     t0 = time.perf_counter()

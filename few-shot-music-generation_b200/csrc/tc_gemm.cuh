@@ -1,20 +1,599 @@
-// tc_gemm.cuh — tcgen05 / TMA / TMEM route of libfsmg (sm_100a).  STUB: filled in next.
+// tc_gemm.cuh — the tcgen05 / TMA / TMEM route of libfsmg (sm_100a only).
+//
+// One persistent, warp-specialised GEMM core (fp16 x fp16 -> fp32 in TMEM) with pluggable epilogues:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
+//   warps 2..5  : epilogue (tcgen05.ld 32x32b, one accumulator row per thread), double-buffered TMEM
+// C[M,N] (op)= alpha * A * B^T with A, B each either K-major (row = m/n, contiguous k) or MN-major
+// (row = k, contiguous m/n) — the latter serves the weight-gradient contractions over tokens.
+//
+// Contractions of the hot path that run here: K3 input GEMM, K4 per-step recurrent GEMM
+// (until the persistent kernel takes over), K5+K7 projection with fused online log-sum-exp / NLL,
+// K8 dgrad / wgrad GEMMs.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "simt_kernels.cuh"
 
 namespace fsmg {
-struct Bump;
-struct TcContext { bool ready = false; };
-template <typename B> static inline void tc_carve(TcContext&, B&, int, int, int, int, int, int) {}
-static inline int tc_init(TcContext& c) { c.ready = true; return 0; }
-static inline bool tc_gemm_supported(const GemmArgs&, bool, bool) { return false; }
-static inline int tc_gemm(TcContext&, const GemmArgs&, bool, bool, cudaStream_t) { return set_error(-1, "tc_gemm stub"); }
+
+namespace tc {
+
+constexpr int BM = 128;      // UMMA M (cta_group::1)
+constexpr int BK = 64;       // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- descriptors ------------------------------------------------------------------------------------
+// Shared-memory matrix descriptor (sm_100 "SmemDescriptor": cute/arch/mma_sm100_desc.hpp):
+//   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor (kind::f16): c_format F32 (bits 4-5 = 1), a/b format F16 (0), a_major bit 15,
+// b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---- epilogue parameter block ----------------------------------------------------------------------
+enum EpiMode { EPI_STORE = 0, EPI_LSE = 1 };
+
+struct EpiParams {
+    // EPI_STORE
+    void* C; int64_t ldc;
+    const float* bias; float alpha;
+    int c_half, accumulate, atomic;
+    // EPI_LSE: logits = acc + bias; per (row, n-tile) online (max, sumexp); target-logit pick; optional fp16 logits
+    float2* part; int n_tiles_total;    // part[row * n_tiles_total + n_blk]
+    const int32_t* y; int64_t row0;     // y[row0 + row]
+    float* tgt;                         // tgt[row]
+    __half* logits16; int64_t ld16;
+};
+
+struct GemmShape {
+    int M, N, K;
+    int n_m, n_n, n_s;      // tiles along M, N and K-splits
+    int kb_per_split;       // k-blocks per split
+    int kb_total;
+};
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;        // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;        // 32 KB (BN=256) / 16 KB (BN=128)
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape sh, EpiParams ep) {
+    using L = SmemLayout<BN>;
+    constexpr int STAGES = L::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = sh.n_m * sh.n_n * sh.n_s;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a);
+        tma_prefetch_desc(&map_b);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_base_slot, 2 * BN);   // 2 accumulator stages of BN fp32 columns
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_blk = tile % sh.n_m, n_blk = (tile / sh.n_m) % sh.n_n, s_blk = tile / (sh.n_m * sh.n_n);
+                const int kb0 = s_blk * sh.kb_per_split;
+                const int kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::A_BYTES;
+                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if (A_MN) {
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &full_bar[stage]);
+                    } else {
+                        tma_load_2d(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                    }
+                    if (B_MN) {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &map_b, n_blk * BN + j * 64, kb * BK, &full_bar[stage]);
+                    } else {
+                        tma_load_2d(sb, &map_b, kb * BK, n_blk * BN, &full_bar[stage]);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int s_blk = tile / (sh.n_m * sh.n_n);
+                const int kb0 = s_blk * sh.kb_per_split;
+                const int kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // K-major SW128: atom = 8 rows x 128 B, SBO = 1024 B, +32 B per UMMA_K inside the swizzle row.
+                        // MN-major SW128: atom = 8 k-rows x 64 mn, SBO = 1024 B (next 8 k), LBO = 8192 B (next 64 mn), +2048 B per UMMA_K.
+                        const uint64_t a_desc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+                        const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+                        umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int m_blk = tile % sh.n_m, n_blk = (tile / sh.n_m) % sh.n_n, s_blk = tile / (sh.n_m * sh.n_n);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            const int row = m_blk * BM + quad * 32 + lane;        // global row of this thread
+            const bool row_ok = row < sh.M;
+            const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+            float run_max = -INFINITY, run_sum = 0.0f;
+            int tgt_col = -1;
+            if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - n_blk * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c * 32, r);
+                tmem_ld_wait();
+                const int col0 = n_blk * BN + c * 32;
+                if (col0 >= sh.N) continue;   // warp-uniform
+                if (EPI == EPI_STORE) {
+                    if (row_ok) {
+                        const bool add_bias = ep.bias != nullptr && s_blk == 0;
+                        const bool full = col0 + 32 <= sh.N;
+                        if (ep.c_half) {
+                            __half* dst = reinterpret_cast<__half*>(ep.C) + (int64_t)row * ep.ldc + col0;
+                            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    __half2 h[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        float v0 = ep.alpha * __uint_as_float(r[j + 2 * q]) + (add_bias ? ep.bias[col0 + j + 2 * q] : 0.0f);
+                                        float v1 = ep.alpha * __uint_as_float(r[j + 2 * q + 1]) + (add_bias ? ep.bias[col0 + j + 2 * q + 1] : 0.0f);
+                                        h[q] = __floats2half2_rn(v0, v1);
+                                    }
+                                    *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(h);
+                                }
+                            } else {
+                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j)
+                                    dst[j] = __float2half_rn(ep.alpha * __uint_as_float(r[j]) + (add_bias ? ep.bias[col0 + j] : 0.0f));
+                            }
+                        } else {
+                            float* dst = reinterpret_cast<float*>(ep.C) + (int64_t)row * ep.ldc + col0;
+                            if (ep.atomic) {
+                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j)
+                                    atomicAdd(dst + j, ep.alpha * __uint_as_float(r[j]) + (add_bias ? ep.bias[col0 + j] : 0.0f));
+                            } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4) {
+                                    float4 v;
+                                    v.x = ep.alpha * __uint_as_float(r[j]);
+                                    v.y = ep.alpha * __uint_as_float(r[j + 1]);
+                                    v.z = ep.alpha * __uint_as_float(r[j + 2]);
+                                    v.w = ep.alpha * __uint_as_float(r[j + 3]);
+                                    if (add_bias) {
+                                        const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+                                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                                    }
+                                    if (ep.accumulate) {
+                                        const float4 o = *reinterpret_cast<const float4*>(dst + j);
+                                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                                    }
+                                    *reinterpret_cast<float4*>(dst + j) = v;
+                                }
+                            } else {
+                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j) {
+                                    float v = ep.alpha * __uint_as_float(r[j]) + (add_bias ? ep.bias[col0 + j] : 0.0f);
+                                    if (ep.accumulate) v += dst[j];
+                                    dst[j] = v;
+                                }
+                            }
+                        }
+                    }
+                } else {  // EPI_LSE
+                    if (row_ok) {
+                        float v[32];
+                        float cmax = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const bool ok = col0 + j < sh.N;
+                            v[j] = ok ? __uint_as_float(r[j]) + ep.bias[col0 + j] : -INFINITY;
+                            cmax = fmaxf(cmax, v[j]);
+                        }
+                        const int tj = tgt_col - c * 32;
+                        if (tj >= 0 && tj < 32) {
+                            float tv = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) tv = (j == tj) ? v[j] : tv;
+                            ep.tgt[row] = tv;
+                        }
+                        const float nmax = fmaxf(run_max, cmax);
+                        float s = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) s += __expf(v[j] - nmax);
+                        run_sum = run_sum * __expf(run_max - nmax) + s;
+                        run_max = nmax;
+                        if (ep.logits16) {
+                            __half* dst = ep.logits16 + (int64_t)row * ep.ld16 + col0;
+                            if (col0 + 32 <= sh.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 8) {
+                                    __half2 h[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[j + 2 * q], v[j + 2 * q + 1]);
+                                    *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(h);
+                                }
+                            } else {
+                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j) dst[j] = __float2half_rn(v[j]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk] = make_float2(run_max, run_sum);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 4 epilogue warps -> count 4
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+}
+
+// combine the per-(row, n-tile) (max, sumexp) partials: lse = M + log(sum_i s_i * exp(m_i - M)); nll = lse - tgt
+__global__ void lse_combine_kernel(const float2* __restrict__ part, int n_tiles, const float* __restrict__ tgt,
+                                   int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
+                                   float* __restrict__ nll_out) {
+    int lr = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lr >= rows) return;
+    const float2* p = part + (int64_t)lr * n_tiles;
+    float m = -INFINITY;
+    for (int i = 0; i < n_tiles; ++i) m = fmaxf(m, p[i].x);
+    float s = 0.0f;
+    for (int i = 0; i < n_tiles; ++i) s += p[i].y * expf(p[i].x - m);
+    float lse = m + logf(s);
+    int64_t r = row0 + lr;
+    if (lse_out) lse_out[r] = lse;
+    int t = (int)(r / N), n = (int)(r % N);
+    if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[lr];
+}
+
+// in place over the fp16 logits chunk: dlogits = exp(logit - lse) - onehot(y)   (unscaled)
+__global__ void softmax_grad_inplace_kernel(__half* __restrict__ logits, int64_t ld, int vp1, const float* __restrict__ lse,
+                                            const int32_t* __restrict__ y, int64_t row0) {
+    int64_t lr = blockIdx.x;
+    __half* row = logits + lr * ld;
+    const float l = lse[row0 + lr];
+    const int tgt = y[row0 + lr];
+    for (int v = threadIdx.x * 2; v < ld; v += blockDim.x * 2) {
+        __half2 h = *reinterpret_cast<__half2*>(row + v);
+        float2 f = __half22float2(h);
+        float a = v < vp1 ? __expf(f.x - l) - (v == tgt ? 1.0f : 0.0f) : 0.0f;
+        float b = v + 1 < vp1 ? __expf(f.y - l) - (v + 1 == tgt ? 1.0f : 0.0f) : 0.0f;
+        *reinterpret_cast<__half2*>(row + v) = __floats2half2_rn(a, b);
+    }
+}
+
+}  // namespace tc
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcContext {
+    bool ready = false;
+    int num_sms = 148;
+    PFN_tensorMapEncodeTiled encode = nullptr;
+    // projection scratch (carved from the caller's workspace)
+    float2* part = nullptr;
+    float* tgt = nullptr;
+    int part_tiles = 0;
+    int enabled = 1;
+};
+
+template <typename B>
+static inline void tc_carve(TcContext& c, B& b, int /*Nmax*/, int /*T*/, int V1, int /*Vp*/, int /*H*/, int chunk_rows) {
+    c.part_tiles = cdiv(V1, 128);
+    c.part = b.template take<float2>((int64_t)chunk_rows * c.part_tiles);
+    c.tgt = b.template take<float>(chunk_rows);
+}
+
+static inline int tc_init(TcContext& c) {
+    if (c.ready) return 0;
+    const char* env = getenv("FSMG_TC");
+    c.enabled = env ? atoi(env) : 1;
+    int dev = 0;
+    FSMG_CUDA_OK(cudaGetDevice(&dev));
+    FSMG_CUDA_OK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FSMG_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return set_error(-2, "cuTensorMapEncodeTiled not available from the driver");
+    c.encode = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
+#define FSMG_SET_SMEM(BN, EPI, AM, BMN)                                                                               \
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      tc::SmemLayout<BN>::TOTAL))
+    FSMG_SET_SMEM(256, tc::EPI_STORE, false, false);
+    FSMG_SET_SMEM(256, tc::EPI_STORE, true, true);
+    FSMG_SET_SMEM(128, tc::EPI_STORE, false, false);
+    FSMG_SET_SMEM(128, tc::EPI_STORE, true, true);
+    FSMG_SET_SMEM(256, tc::EPI_LSE, false, false);
+    FSMG_SET_SMEM(128, tc::EPI_LSE, false, false);
+#undef FSMG_SET_SMEM
+    c.ready = true;
+    return 0;
+}
+
+// fp16 2-D tensor map with 128-byte swizzle.  inner = contiguous extent (elements), outer = rows, ld in elements.
+static inline int make_map_f16(const TcContext& c, CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                               uint32_t box_inner, uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {ld * 2};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = c.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return set_error(-2, "cuTensorMapEncodeTiled failed (%d): base=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, base,
+                         (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return 0;
+}
+
+static inline bool tc_operands_ok(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (ld % 8) == 0; }
+
+static inline bool tc_gemm_supported(const GemmArgs& g, bool a_mn, bool b_mn) {
+    if (a_mn != b_mn) return false;  // only NT (both K-major) and TN-of-tokens (both MN-major) occur on the hot path
+    if (!tc_operands_ok(g.A, g.lda) || !tc_operands_ok(g.B, g.ldb)) return false;
+    if (g.c_half && g.accumulate) return false;
+    const char* env = getenv("FSMG_TC");
+    if (env && atoi(env) == 0) return false;
+    return true;
+}
+
+struct TcPlan {
+    int bn;
+    tc::GemmShape sh;
+    int grid;
+};
+
+static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split) {
+    TcPlan p;
+    p.bn = (N > 128) ? 256 : 128;
+    tc::GemmShape& sh = p.sh;
+    sh.M = M; sh.N = N; sh.K = K;
+    sh.n_m = cdiv(M, tc::BM);
+    sh.n_n = cdiv(N, p.bn);
+    sh.kb_total = cdiv(K, tc::BK);
+    int tiles = sh.n_m * sh.n_n;
+    int split = 1;
+    if (allow_split && tiles < c.num_sms) {
+        split = c.num_sms / tiles;                       // fill the machine once
+        int max_split = sh.kb_total / 8;                 // keep >= 8 k-blocks (512 k) per slice
+        if (split > max_split) split = max_split;
+        if (split < 1) split = 1;
+    }
+    sh.kb_per_split = cdiv(sh.kb_total, split);
+    sh.n_s = cdiv(sh.kb_total, sh.kb_per_split);
+    int total = tiles * sh.n_s;
+    p.grid = total < c.num_sms ? total : c.num_sms;
+    return p;
+}
+
+template <int EPI>
+static inline int tc_launch(const TcContext& c, const TcPlan& p, const CUtensorMap& ma, const CUtensorMap& mb, bool mn,
+                            const tc::EpiParams& ep, cudaStream_t s) {
+#define FSMG_GO(BN, MN)                                                                                                   \
+    tc::tc_gemm_kernel<BN, EPI, MN, MN><<<p.grid, tc::NUM_THREADS, tc::SmemLayout<BN>::TOTAL, s>>>(ma, mb, p.sh, ep)
+    if constexpr (EPI == tc::EPI_LSE) {
+        if (p.bn == 256) FSMG_GO(256, false); else FSMG_GO(128, false);
+    } else {
+        if (!mn) { if (p.bn == 256) FSMG_GO(256, false); else FSMG_GO(128, false); }
+        else { if (p.bn == 256) FSMG_GO(256, true); else FSMG_GO(128, true); }
+    }
+#undef FSMG_GO
+    FSMG_LAUNCH_OK();
+    return 0;
+}
+
+static inline int tc_make_maps(const TcContext& c, const GemmArgs& g, bool mn, int bn, CUtensorMap* ma, CUtensorMap* mb) {
+    int rc;
+    if (!mn) {
+        if ((rc = make_map_f16(c, ma, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, tc::BK, tc::BM))) return rc;
+        if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, tc::BK, (uint32_t)bn))) return rc;
+    } else {
+        if ((rc = make_map_f16(c, ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 64, tc::BK))) return rc;
+        if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 64, tc::BK))) return rc;
+    }
+    return 0;
+}
+
+static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn, cudaStream_t s) {
+    (void)b_mn;
+    if (!c.ready) return set_error(-3, "tcgen05 context not initialised");
+    const bool can_split = !g.c_half && !g.accumulate;   // split-K partials are combined with fp32 atomics
+    TcPlan p = tc_plan(c, g.M, g.N, g.K, can_split);
+    tc::EpiParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.C = g.C; ep.ldc = g.ldc; ep.bias = g.bias; ep.alpha = g.alpha; ep.c_half = g.c_half; ep.accumulate = g.accumulate;
+    ep.atomic = g.atomic;
+    if (p.sh.n_s > 1 && !g.atomic) {
+        // plain store with split-K: zero the destination, then accumulate atomically
+        FSMG_CUDA_OK(cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s));
+        ep.atomic = 1;
+    }
+    CUtensorMap ma, mb;
+    int rc = tc_make_maps(c, g, a_mn, p.bn, &ma, &mb);
+    if (rc) return rc;
+    return tc_launch<tc::EPI_STORE>(c, p, ma, mb, a_mn, ep, s);
+}
+
+// ---- projection forward: logits tile -> online LSE partials (+ fp16 logits when training) -------------
+static inline bool tc_projection_supported(TcContext& c, int H, int V1) {
+    (void)V1;
+    return c.ready && c.enabled && (H % 8 == 0 || true);
+}
+
+static inline int tc_projection_fwd(TcContext& c, const __half* hc, int64_t ldh, const __half* WsT16, int64_t ldw, const float* sb,
+                                    const int32_t* y, int64_t row0, int mc, int N, int T, int H, int V1, __half* logits16,
+                                    int64_t ld16, float* lse, float* nll_out, cudaStream_t s) {
+    GemmArgs g;
+    memset(&g, 0, sizeof g);
+    g.M = mc; g.N = V1; g.K = H; g.A = hc; g.lda = ldh; g.B = WsT16; g.ldb = ldw;
+    if (!tc_operands_ok(g.A, g.lda) || !tc_operands_ok(g.B, g.ldb)) return set_error(-1, "projection operands not TMA-aligned");
+    TcPlan p = tc_plan(c, mc, V1, H, false);
+    tc::EpiParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.bias = sb; ep.part = c.part; ep.n_tiles_total = p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
+    ep.logits16 = logits16; ep.ld16 = ld16;
+    CUtensorMap ma, mb;
+    int rc = tc_make_maps(c, g, false, p.bn, &ma, &mb);
+    if (rc) return rc;
+    rc = tc_launch<tc::EPI_LSE>(c, p, ma, mb, false, ep, s);
+    if (rc) return rc;
+    tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, p.sh.n_n, c.tgt, row0, mc, N, T, lse, nll_out);
+    if (logits16) tc::softmax_grad_inplace_kernel<<<mc, 256, 0, s>>>(logits16, ld16, V1, lse, y, row0);
+    FSMG_LAUNCH_OK();
+    return 0;
+}
+
+// ---- persistent recurrent kernels and the on-device sampler: added in a later milestone --------------------
 static inline bool tc_recurrent_supported(TcContext&, int, int) { return false; }
-static inline int tc_lstm_forward(TcContext&, const float*, const __half*, __half*, float*, __half*, int, int, int, int, int, cudaStream_t) { return set_error(-1, "stub"); }
-static inline int tc_lstm_backward(TcContext&, const float*, const __half*, const __half*, const float*, __half*, int, int, int, int, cudaStream_t) { return set_error(-1, "stub"); }
-static inline bool tc_projection_supported(TcContext&, int, int) { return false; }
-static inline int tc_projection_fwd(TcContext&, const __half*, int64_t, const __half*, int64_t, const float*, const int32_t*, int64_t, int, int, int, int, int, __half*, int64_t, float*, float*, cudaStream_t) { return set_error(-1, "stub"); }
+static inline int tc_lstm_forward(TcContext&, const float*, const __half*, __half*, float*, __half*, int, int, int, int, int, cudaStream_t) { return set_error(-1, "persistent LSTM forward not built"); }
+static inline int tc_lstm_backward(TcContext&, const float*, const __half*, const __half*, const float*, __half*, int, int, int, int, cudaStream_t) { return set_error(-1, "persistent LSTM backward not built"); }
 static inline bool tc_sampler_supported(TcContext&, int, int) { return false; }
-static inline int tc_sample_greedy(TcContext&, int, int, int32_t*, cudaStream_t) { return set_error(-1, "stub"); }
+static inline int tc_sample_greedy(TcContext&, int, int, int32_t*, cudaStream_t) { return set_error(-1, "persistent sampler not built"); }
+
 }  // namespace fsmg

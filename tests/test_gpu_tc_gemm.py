@@ -1,0 +1,58 @@
+"""GPU unit tests of the tcgen05/TMA/TMEM GEMM core through the C-ABI debug entry
+(fsmg_debug_gemm): fp16 operands, fp32 accumulation, against torch fp32 matmul of the same
+fp16-rounded inputs, for K-major (NT) and MN-major (TN-over-tokens) operands, ragged edges and
+split-K."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    # (M, N, K)
+    (128, 256, 64), (128, 128, 64), (256, 512, 512), (200, 300, 136), (45, 800, 248), (1440, 2048, 512),
+    (130, 10008, 512), (2304, 512, 10008), (512, 2048, 9000), (77, 40, 72),
+]
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from fsmg import _lib
+    return _lib.load()
+
+
+def run_gemm(lib, torch, m, n, k, mn, simt=0, seed=0):
+    from fsmg import _lib
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = (torch.rand((k, m) if mn else (m, k), device="cuda", generator=g) - 0.5).half()
+    b = (torch.rand((k, n) if mn else (n, k), device="cuda", generator=g) - 0.5).half()
+    c = torch.full((m, n), float("nan"), device="cuda", dtype=torch.float32)
+    _lib.check(lib.fsmg_debug_gemm(m, n, k, a.data_ptr(), b.data_ptr(), c.data_ptr(), int(mn), int(mn), simt,
+                                   torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    ref = (a.float().t() @ b.float()) if mn else (a.float() @ b.float().t())
+    return c, ref
+
+
+@pytest.mark.parametrize("mn", [False, True], ids=["k_major", "mn_major"])
+@pytest.mark.parametrize("shape", SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_tcgen05_gemm_matches_fp32_matmul(lib, shape, mn):
+    import torch
+    m, n, k = shape
+    if mn and (m % 8 or n % 8):
+        pytest.skip("MN-major operands need leading dimensions that are multiples of 8")
+    if not mn and k % 8:
+        pytest.skip("K-major operands need K % 8 == 0")
+    c, ref = run_gemm(lib, torch, m, n, k, mn)
+    err = (c - ref).abs().max().item()
+    assert torch.isfinite(c).all()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_simt_gemm_matches_too(lib):
+    import torch
+    for mn in (False, True):
+        c, ref = run_gemm(lib, torch, 200, 304, 136, mn, simt=1)
+        assert (c - ref).abs().max().item() < 1e-3
