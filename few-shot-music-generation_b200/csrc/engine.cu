@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "simt_kernels.cuh"
 #include "tc_gemm.cuh"
+#include "tc_lstm.cuh"
 
 namespace fsmg {
 

@@ -420,6 +420,7 @@ struct TcContext {
     float2* part = nullptr;
     float* tgt = nullptr;
     int part_tiles = 0;
+    int* counters = nullptr;   // [256] group-progress counters of the persistent recurrent kernels
     int enabled = 1;
 };
 
@@ -428,6 +429,7 @@ static inline void tc_carve(TcContext& c, B& b, int /*Nmax*/, int /*T*/, int V1,
     c.part_tiles = cdiv(V1, 128);
     c.part = b.template take<float2>((int64_t)chunk_rows * c.part_tiles);
     c.tgt = b.template take<float>(chunk_rows);
+    c.counters = b.template take<int>(256);
 }
 
 static inline int tc_init(TcContext& c) {
@@ -588,12 +590,5 @@ static inline int tc_projection_fwd(TcContext& c, const __half* hc, int64_t ldh,
     FSMG_LAUNCH_OK();
     return 0;
 }
-
-// ---- persistent recurrent kernels and the on-device sampler: added in a later milestone --------------------
-static inline bool tc_recurrent_supported(TcContext&, int, int) { return false; }
-static inline int tc_lstm_forward(TcContext&, const float*, const __half*, __half*, float*, __half*, int, int, int, int, int, cudaStream_t) { return set_error(-1, "persistent LSTM forward not built"); }
-static inline int tc_lstm_backward(TcContext&, const float*, const __half*, const __half*, const float*, __half*, int, int, int, int, cudaStream_t) { return set_error(-1, "persistent LSTM backward not built"); }
-static inline bool tc_sampler_supported(TcContext&, int, int) { return false; }
-static inline int tc_sample_greedy(TcContext&, int, int, int32_t*, cudaStream_t) { return set_error(-1, "persistent sampler not built"); }
 
 }  // namespace fsmg

@@ -1,0 +1,590 @@
+// tc_lstm.cuh — persistent-RNN kernels (sm_100a): the T-step recurrence of BasicLSTMCell
+// (reference src/models/lstm_baseline.py:44-55, [TF-lib] A.2/A.3) and its reverse-time backward, ONE
+// launch per direction instead of T launches.
+//
+// Decomposition.  The N sequences are split into G independent groups; a group is served by
+// C = H/U CTAs, CTA j owning hidden units [jU, (j+1)U) — all four gates of those units, so the cell
+// update is CTA-local.  Its slice of the recurrent weights (fp16; 128 KB for U=32, H=512) is loaded
+// ONCE by TMA and stays resident in shared memory for all T steps.  Per step:
+//   producer warp : waits until the group's C CTAs have published the previous step (monotonic counter
+//                   in L2, release/acquire), then streams the exchanged operand (h_{t-1} forward,
+//                   dgates_{t+1} backward) through a TMA ring (SWIZZLE_128B);
+//   MMA warp      : tcgen05.mma (M=128, N=4U forward / U backward, K=16), accumulators in TMEM;
+//   epilogue warps: tcgen05.ld -> cell math in fp32 -> state (c forward, dc backward) kept in REGISTERS
+//                   for the whole sequence -> writes the step's outputs -> publishes.
+// Groups never synchronise with each other: no grid-wide barrier.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace fsmg {
+namespace tc {
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// 2*sigmoid(2x)-1: absolute error ~2e-7 (ex2.approx + rcp.approx), far below the fp16 rounding of h
+__device__ __forceinline__ float tanh_fast(float x) { return __fdividef(2.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+struct LstmParams {
+    // forward
+    const float* pre;      // [T*N, 4H] fp32: x_t * Wx + b (hoisted input contraction)
+    // backward
+    const float* dh_out;   // [T*N, H] fp32: dL/dh_t from above (projection or upper layer), unscaled
+    __half* dgates;        // [T*N, G4p] fp16 out (also the exchanged operand)
+    // shared
+    __half* gates;         // [T*N, G4p] fp16 post-activation i|j|f|o (stash: written fwd, read bwd)
+    float* c;              // [T*N, H]
+    __half* hs;            // [T*N, Hp]   (fwd out)
+    int* counters;         // [G] monotonic counters (zeroed by the host before the launch)
+    int N, T, H, Hp, G4p;
+    int ctas_per_group, rows_per_group, box_rows;   // C, M_g, TMA box rows (= M_g rounded to 8)
+    int row_offset;        // first sequence handled by this launch (batch slicing when N is large)
+    int n_rows;            // sequences handled by this launch
+};
+
+constexpr int LSTM_THREADS = 64 + 128;   // producer warp, MMA warp, 4 epilogue warps
+constexpr int LSTM_MAX_DYN = 227 * 1024;
+
+// smem: [resident weights: KCW chunks x CHUNK_W bytes] [ring: STAGES x (MT*128 rows x 128 B)] [barriers]
+__host__ __device__ constexpr int lstm_stage_bytes(int mt) { return mt * 128 * 128; }
+__host__ __device__ constexpr int lstm_num_stages(int w_bytes, int mt) {
+    int s = (LSTM_MAX_DYN - 1024 - 256 - w_bytes) / lstm_stage_bytes(mt);
+    return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr int lstm_smem_total(int w_bytes, int mt) {
+    return 1024 + 256 + w_bytes + lstm_num_stages(w_bytes, mt) * lstm_stage_bytes(mt);
+}
+__host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
+
+// =====================================================================================================
+// forward
+// =====================================================================================================
+template <int U, int MT>
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, LstmParams p) {
+    constexpr int NCOL = 4 * U;                 // accumulator columns per row tile (UMMA N)
+    constexpr int CHUNK_W = NCOL * 128;         // bytes of the weight slice per 64-wide K chunk
+    const int KC = p.H / 64;
+    const int W_BYTES = KC * CHUNK_W;
+    const int STAGES = lstm_num_stages(W_BYTES, MT);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;
+    uint8_t* sA = sW + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * lstm_stage_bytes(MT));
+    uint64_t* full_bar = bars;                  // [8]
+    uint64_t* empty_bar = bars + 8;             // [8]
+    uint64_t* w_bar = bars + 16;
+    uint64_t* tmem_full = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
+    const int row_base = p.row_offset + g * p.rows_per_group;                       // first sequence of the group
+    const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);     // sequences present (>= 1)
+    int* counter = p.counters + g;
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_h);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(w_bar, 1);
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // resident weights: per K chunk the 4 gate blocks of U rows -> smem rows [i(U) | j(U) | f(U) | o(U)]
+            mbar_expect_tx(w_bar, (uint32_t)W_BYTES);
+            for (int kc = 0; kc < KC; ++kc)
+                for (int q = 0; q < 4; ++q)
+                    tma_load_2d(sW + kc * CHUNK_W + q * U * 128, &map_w, kc * 64, q * p.H + j * U, w_bar);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;
+            for (int t = 1; t < p.T; ++t) {
+                const int need = p.ctas_per_group * t;      // all C CTAs of the group have published h_{t-1}
+                while (ld_acquire(counter) < need) { }
+                fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], box_bytes);
+                    tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NCOL, false, false);
+            mbar_wait(w_bar, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 1; t < p.T; ++t) {
+                // (TMEM reuse is safe: the loads of step t are only issued after this CTA's own epilogue of
+                //  step t-1 has drained the accumulators and published through the counter.)
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(sA + stage * lstm_stage_bytes(MT));
+                    const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
+                            const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
+                            umma_f16(tmem_base + mt * NCOL, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full);
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> (row tile mt, TMEM lane); the cell state c stays in registers for all T steps
+        const int quad = warp & 3;
+        float c_state[MT][U];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int u = 0; u < U; ++u) c_state[mt][u] = 0.0f;
+        uint32_t tf_phase = 0;
+        for (int t = 0; t < p.T; ++t) {
+            if (t + 1 < p.T) {   // pull next step's pre-activation lines towards L2 while this step computes
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int lrow = mt * 128 + quad * 32 + lane;
+                    if (lrow < rows) {
+                        const float* nxt = p.pre + ((int64_t)(t + 1) * p.N + row_base + lrow) * (4 * p.H) + j * U;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
+                    }
+                }
+            }
+            if (t > 0) {
+                mbar_wait(tmem_full, tf_phase);
+                tf_phase ^= 1;
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int lrow = mt * 128 + quad * 32 + lane;         // row inside the group
+                const bool ok = lrow < rows;
+                const int64_t r = (int64_t)t * p.N + row_base + lrow; // time-major token row
+                const float* pre = p.pre + r * (4 * p.H) + j * U;
+                __half* gout = p.gates + r * p.G4p + j * U;
+                const uint32_t t_row = tmem_base + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+                for (int u0 = 0; u0 < U; u0 += 8) {
+                    float acc[4][8];
+                    if (t > 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t rr[8];
+                            tmem_ld8(t_row + q * U + u0, rr);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[q][e] = __uint_as_float(rr[e]);
+                        }
+                        tmem_ld_wait();
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[q][e] = 0.0f;
+                    }
+                    if (ok) {
+                        float pg[4][8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 a = *reinterpret_cast<const float4*>(pre + q * p.H + u0);
+                            const float4 b = *reinterpret_cast<const float4*>(pre + q * p.H + u0 + 4);
+                            pg[q][0] = a.x; pg[q][1] = a.y; pg[q][2] = a.z; pg[q][3] = a.w;
+                            pg[q][4] = b.x; pg[q][5] = b.y; pg[q][6] = b.z; pg[q][7] = b.w;
+                        }
+                        __align__(16) __half hq[4][8];
+                        __align__(16) __half hh[8];
+                        float cn[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float i_ = sigmoid_fast(pg[0][e] + acc[0][e]);
+                            const float j_ = tanh_fast(pg[1][e] + acc[1][e]);
+                            const float f_ = sigmoid_fast(pg[2][e] + acc[2][e] + 1.0f);   // forget_bias = 1 (A.2)
+                            const float o_ = sigmoid_fast(pg[3][e] + acc[3][e]);
+                            const float cv = c_state[mt][u0 + e] * f_ + i_ * j_;
+                            c_state[mt][u0 + e] = cv;
+                            cn[e] = cv;
+                            hq[0][e] = __float2half_rn(i_); hq[1][e] = __float2half_rn(j_);
+                            hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
+                            hh[e] = __float2half_rn(tanh_fast(cv) * o_);
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(gout + q * p.H + u0) = *reinterpret_cast<uint4*>(hq[q]);
+                        *reinterpret_cast<uint4*>(p.hs + r * p.Hp + j * U + u0) = *reinterpret_cast<uint4*>(hh);
+                        float* cdst = p.c + r * p.H + j * U + u0;
+                        *reinterpret_cast<float4*>(cdst) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                        *reinterpret_cast<float4*>(cdst + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __threadfence();                      // this thread's h_t / stash stores are visible GPU-wide
+            named_bar_sync(1, 128);
+            if (warp == 2 && lane == 0) red_release_add(counter, 1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// =====================================================================================================
+// backward (reverse time).  Resident: rows [jU, (jU+U)) of kernel[in:, :] (each 4H long, K-major);
+// exchanged operand: dgates_{t+1} [rows, 4H];  accumulator: dh_rec[rows, U].
+//   dh = dh_out[t] + dh_rec ; do = dh*tanh(c) ; dc = dh*o*(1-tanh(c)^2) + dc_next
+//   dgi = dc*j*i(1-i) ; dgj = dc*i*(1-j^2) ; dgf = dc*c_prev*f(1-f) ; dgo = do*o(1-o) ; dc_next' = dc*f
+// =====================================================================================================
+template <int U, int MT>
+__global__ void __launch_bounds__(LSTM_THREADS, 1)
+lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dg, LstmParams p) {
+    constexpr int NCOL = U;
+    constexpr int CHUNK_W = U * 128;
+    const int KC = (4 * p.H) / 64;
+    const int W_BYTES = KC * CHUNK_W;
+    const int STAGES = lstm_num_stages(W_BYTES, MT);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sW = smem;
+    uint8_t* sA = sW + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * lstm_stage_bytes(MT));
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* w_bar = bars + 16;
+    uint64_t* tmem_full = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
+    const int row_base = p.row_offset + g * p.rows_per_group;
+    const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);
+    int* counter = p.counters + g;
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_dg);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(w_bar, 1);
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)W_BYTES);
+            for (int kc = 0; kc < KC; ++kc) tma_load_2d(sW + kc * CHUNK_W, &map_w, kc * 64, j * U, w_bar);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t box_bytes = (uint32_t)p.box_rows * 128u;
+            for (int s = 1; s < p.T; ++s) {             // s-th processed step handles t = T-1-s and needs dgates_{t+1}
+                const int t = p.T - 1 - s;
+                while (ld_acquire(counter) < p.ctas_per_group * s) { }
+                fence_proxy_async_all();
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], box_bytes);
+                    tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NCOL, false, false);
+            mbar_wait(w_bar, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 1; s < p.T; ++s) {
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(sA + stage * lstm_stage_bytes(MT));
+                    const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
+                            const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
+                            umma_f16(tmem_base + mt * NCOL, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tmem_full);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        float dc_state[MT][U];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int u = 0; u < U; ++u) dc_state[mt][u] = 0.0f;
+        uint32_t tf_phase = 0;
+        for (int s = 0; s < p.T; ++s) {
+            const int t = p.T - 1 - s;
+            if (s > 0) {
+                mbar_wait(tmem_full, tf_phase);
+                tf_phase ^= 1;
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int lrow = mt * 128 + quad * 32 + lane;
+                const bool ok = lrow < rows;
+                const int64_t r = (int64_t)t * p.N + row_base + lrow;
+                const __half* gin = p.gates + r * p.G4p + j * U;
+                __half* dgo = p.dgates + r * p.G4p + j * U;
+                const uint32_t t_row = tmem_base + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+                for (int u0 = 0; u0 < U; u0 += 8) {
+                    float acc[8];
+                    if (s > 0) {
+                        uint32_t rr[8];
+                        tmem_ld8(t_row + u0, rr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(rr[e]);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+                    }
+                    if (ok) {
+                        __align__(16) __half hq[4][8];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(hq[q]) = *reinterpret_cast<const uint4*>(gin + q * p.H + u0);
+                        const float* dho = p.dh_out + r * p.H + j * U + u0;
+                        const float* cc = p.c + r * p.H + j * U + u0;
+                        float dh[8], cv[8], cp[8];
+                        {
+                            const float4 a = *reinterpret_cast<const float4*>(dho), b = *reinterpret_cast<const float4*>(dho + 4);
+                            dh[0] = a.x; dh[1] = a.y; dh[2] = a.z; dh[3] = a.w; dh[4] = b.x; dh[5] = b.y; dh[6] = b.z; dh[7] = b.w;
+                            const float4 c0 = *reinterpret_cast<const float4*>(cc), c1 = *reinterpret_cast<const float4*>(cc + 4);
+                            cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
+                            if (t > 0) {
+                                const float* cpp = cc - (int64_t)p.N * p.H;
+                                const float4 p0 = *reinterpret_cast<const float4*>(cpp), p1 = *reinterpret_cast<const float4*>(cpp + 4);
+                                cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w; cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) cp[e] = 0.0f;
+                            }
+                        }
+                        __align__(16) __half dq[4][8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float i_ = __half2float(hq[0][e]), j_ = __half2float(hq[1][e]);
+                            const float f_ = __half2float(hq[2][e]), o_ = __half2float(hq[3][e]);
+                            const float dhv = dh[e] + acc[e];
+                            const float tcv = tanh_fast(cv[e]);
+                            const float d_o = dhv * tcv;
+                            const float dc = dhv * o_ * (1.0f - tcv * tcv) + dc_state[mt][u0 + e];
+                            dq[0][e] = __float2half_rn(dc * j_ * i_ * (1.0f - i_));
+                            dq[1][e] = __float2half_rn(dc * i_ * (1.0f - j_ * j_));
+                            dq[2][e] = __float2half_rn(dc * cp[e] * f_ * (1.0f - f_));
+                            dq[3][e] = __float2half_rn(d_o * o_ * (1.0f - o_));
+                            dc_state[mt][u0 + e] = dc * f_;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dgo + q * p.H + u0) = *reinterpret_cast<uint4*>(dq[q]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __threadfence();
+            named_bar_sync(1, 128);
+            if (warp == 2 && lane == 0) red_release_add(counter, 1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace tc
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+struct LstmPlan {
+    int U, MT, C, G, rows_per_group, box_rows, rows_per_launch;
+    bool ok;
+};
+
+static inline LstmPlan lstm_plan(const TcContext& c, int N, int H) {
+    LstmPlan pl;
+    memset(&pl, 0, sizeof pl);
+    pl.ok = false;
+    if (H % 64 != 0 || H < 64) return pl;
+    int U = 0;
+    if (4 * 32 * H * 2 <= 128 * 1024 && H % 32 == 0) U = 32;
+    else if (4 * 16 * H * 2 <= 128 * 1024 && H % 16 == 0) U = 16;
+    if (!U) return pl;
+    pl.U = U;
+    pl.C = H / U;
+    int gmax = c.num_sms / pl.C;
+    if (gmax < 1) return pl;
+    int mg = cdiv(N, gmax);
+    if (mg > 256) mg = 256;                       // larger batches are processed in slices of gmax*256 sequences
+    mg = (int)round_up(mg, 8);
+    pl.rows_per_group = mg;
+    pl.box_rows = mg;
+    pl.MT = mg > 128 ? 2 : 1;
+    pl.rows_per_launch = gmax * mg;
+    pl.G = gmax;
+    pl.ok = true;
+    return pl;
+}
+
+static inline int make_map_f16_3d(const TcContext& c, CUtensorMap* map, const void* base, uint64_t d0, uint64_t d1, uint64_t d2,
+                                  uint64_t ld1, uint64_t ld2, uint32_t b0, uint32_t b1) {
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {ld1 * 2, ld2 * 2};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = c.encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(-2, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+    return 0;
+}
+
+template <typename K>
+static inline int lstm_launch(K kernel, int grid, int smem_bytes, const CUtensorMap& mw, const CUtensorMap& mx, const tc::LstmParams& p,
+                              cudaStream_t s) {
+    FSMG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::LSTM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they wait on each other's counters
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FSMG_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, mw, mx, p));
+    return 0;
+}
+
+static inline bool tc_recurrent_supported(TcContext& c, int N, int H) {
+    if (!c.ready || !c.enabled || !c.counters) return false;
+    const char* env = getenv("FSMG_PERSISTENT");
+    if (env && atoi(env) == 0) return false;
+    return lstm_plan(c, N, H).ok;
+}
+
+// pre [T*N,4H] fp32, WhT16 [4H,Hp] fp16 -> gates [T*N,G4p], c [T*N,H], hs [T*N,Hp]
+static inline int tc_lstm_forward(TcContext& c, const float* pre, const __half* WhT16, __half* gates, float* cbuf, __half* hs, int N,
+                                  int T, int H, int Hp, int G4p, cudaStream_t s) {
+    LstmPlan pl = lstm_plan(c, N, H);
+    if (!pl.ok) return set_error(-1, "persistent LSTM: unsupported shape N=%d H=%d", N, H);
+    CUtensorMap mw, mh;
+    int rc = make_map_f16(c, &mw, WhT16, (uint64_t)H, (uint64_t)4 * H, (uint64_t)Hp, 64, (uint32_t)pl.U);
+    if (rc) return rc;
+    rc = make_map_f16_3d(c, &mh, hs, (uint64_t)H, (uint64_t)N, (uint64_t)T, (uint64_t)Hp, (uint64_t)N * Hp, 64, (uint32_t)pl.box_rows);
+    if (rc) return rc;
+    for (int off = 0; off < N; off += pl.rows_per_launch) {
+        int n_rows = N - off < pl.rows_per_launch ? N - off : pl.rows_per_launch;
+        int G = cdiv(n_rows, pl.rows_per_group);
+        FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
+        tc::LstmParams p;
+        memset(&p, 0, sizeof p);
+        p.pre = pre; p.gates = gates; p.c = cbuf; p.hs = hs; p.counters = c.counters;
+        p.N = N; p.T = T; p.H = H; p.Hp = Hp; p.G4p = G4p;
+        p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
+        const int w_bytes = (H / 64) * 4 * pl.U * 128;
+        const int smem = tc::lstm_smem_total(w_bytes, pl.MT);
+        if (pl.U == 32 && pl.MT == 2) rc = lstm_launch(tc::lstm_fwd_persistent_kernel<32, 2>, G * pl.C, smem, mw, mh, p, s);
+        else if (pl.U == 32) rc = lstm_launch(tc::lstm_fwd_persistent_kernel<32, 1>, G * pl.C, smem, mw, mh, p, s);
+        else if (pl.MT == 2) rc = lstm_launch(tc::lstm_fwd_persistent_kernel<16, 2>, G * pl.C, smem, mw, mh, p, s);
+        else rc = lstm_launch(tc::lstm_fwd_persistent_kernel<16, 1>, G * pl.C, smem, mw, mh, p, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// dh_out [T*N,H] fp32, Wh_rows = kernel[in:, :] fp16 [H, G4p] -> dgates [T*N,G4p]
+static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __half* Wh_rows, const __half* gates, const float* cbuf,
+                                   __half* dgates, int N, int T, int H, int G4p, cudaStream_t s) {
+    LstmPlan pl = lstm_plan(c, N, H);
+    if (!pl.ok) return set_error(-1, "persistent LSTM: unsupported shape N=%d H=%d", N, H);
+    CUtensorMap mw, md;
+    int rc = make_map_f16(c, &mw, Wh_rows, (uint64_t)4 * H, (uint64_t)H, (uint64_t)G4p, 64, (uint32_t)pl.U);
+    if (rc) return rc;
+    rc = make_map_f16_3d(c, &md, dgates, (uint64_t)4 * H, (uint64_t)N, (uint64_t)T, (uint64_t)G4p, (uint64_t)N * G4p, 64, (uint32_t)pl.box_rows);
+    if (rc) return rc;
+    for (int off = 0; off < N; off += pl.rows_per_launch) {
+        int n_rows = N - off < pl.rows_per_launch ? N - off : pl.rows_per_launch;
+        int G = cdiv(n_rows, pl.rows_per_group);
+        FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
+        tc::LstmParams p;
+        memset(&p, 0, sizeof p);
+        p.dh_out = dh_out; p.dgates = dgates; p.gates = const_cast<__half*>(gates); p.c = const_cast<float*>(cbuf); p.counters = c.counters;
+        p.N = N; p.T = T; p.H = H; p.Hp = 0; p.G4p = G4p;
+        p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
+        const int w_bytes = (4 * H / 64) * pl.U * 128;
+        const int smem = tc::lstm_smem_total(w_bytes, pl.MT);
+        if (pl.U == 32 && pl.MT == 2) rc = lstm_launch(tc::lstm_bwd_persistent_kernel<32, 2>, G * pl.C, smem, mw, md, p, s);
+        else if (pl.U == 32) rc = lstm_launch(tc::lstm_bwd_persistent_kernel<32, 1>, G * pl.C, smem, mw, md, p, s);
+        else if (pl.MT == 2) rc = lstm_launch(tc::lstm_bwd_persistent_kernel<16, 2>, G * pl.C, smem, mw, md, p, s);
+        else rc = lstm_launch(tc::lstm_bwd_persistent_kernel<16, 1>, G * pl.C, smem, mw, md, p, s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// on-device greedy sampler: added in a later milestone
+static inline bool tc_sampler_supported(TcContext&, int, int) { return false; }
+static inline int tc_sample_greedy(TcContext&, int, int, int32_t*, cudaStream_t) { return set_error(-1, "persistent sampler not built"); }
+
+}  // namespace fsmg
