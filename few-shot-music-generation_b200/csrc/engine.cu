@@ -49,8 +49,24 @@ struct LayerBuf {
 
 using namespace fsmg;
 
+enum ProfPhase { PH_PREP = 0, PH_INPUT_GEMM, PH_REC_FWD, PH_PROJ_FWD, PH_SOFTMAX_GRAD, PH_DH, PH_DWS, PH_REC_BWD, PH_WGRAD, PH_DX, PH_UPDATE, PH_COUNT };
+static const char* kPhaseNames[PH_COUNT] = {"prep_gather", "input_gemm", "recurrent_fwd", "proj_logits_lse", "softmax_grad_bias", "proj_dh",
+                                            "proj_dws", "recurrent_bwd", "wgrad_kernel_bias", "dx_scatter", "clip_adam_refresh"};
+struct ProfState {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Rec { int ph; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+};
+
 struct fsmg_handle {
     fsmg_config cfg;
+    ProfState prof;
     std::string scope;
     int V = 0, V1 = 0, E = 0, H = 0, L = 0, T = 0, Nmax = 0;
     int Ep = 0, Hp = 0, G4 = 0, G4p = 0, Vp = 0;
@@ -68,7 +84,7 @@ struct fsmg_handle {
     int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *samp_ids = nullptr, *samp_out = nullptr;
     __half *emb16 = nullptr, *Ws16 = nullptr, *WsT16 = nullptr, *xemb = nullptr, *dgates = nullptr, *dlogits = nullptr;
     float *pre = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
-    float *lse = nullptr, *nll = nullptr, *scalars = nullptr;
+    float *lse = nullptr, *nll = nullptr, *scalars = nullptr, *dws_acc = nullptr;
     float *s_x = nullptr, *s_g = nullptr, *s_logits = nullptr;
     std::vector<float*> s_c, s_h;
     int chunk_rows = 0;
@@ -84,6 +100,17 @@ struct fsmg_handle {
 namespace fsmg {
 
 #define LAUNCH_COUNT(h) ((h)->launches++)
+
+// brackets a phase with CUDA events on the launching stream when profiling is enabled
+struct ProfScope {
+    fsmg_handle* h; cudaStream_t s; int ph; cudaEvent_t a = nullptr;
+    ProfScope(fsmg_handle* h_, int ph_, cudaStream_t s_) : h(h_), s(s_), ph(ph_) {
+        if (h->prof.on) { a = h->prof.get(); cudaEventRecord(a, s); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEvent_t b = h->prof.get(); cudaEventRecord(b, s); h->prof.recs.push_back({ph, a, b}); }
+    }
+};
 
 // bump allocator used twice: sizing (base == nullptr) and carving
 struct Bump {
@@ -134,6 +161,7 @@ static void carve(fsmg_handle* h, char* base) {
     h->chunk_rows = (int)rows;
     h->logits32 = b.take<float>(rows * h->Vp);
     h->dlogits = b.take<__half>(rows * h->Vp);
+    h->dws_acc = b.take<float>((int64_t)h->H * h->Vp);   // dWs accumulated with 16-byte aligned rows (V' is odd)
     // sampler (fp32 route)
     h->samp_max = h->Nmax;
     h->samp_ids = b.take<int32_t>(h->samp_max);
@@ -202,9 +230,10 @@ static int refresh_weights(fsmg_handle* h, cudaStream_t s) {
 static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, cudaStream_t s) {
     const int T = h->T, H = h->H, TB = 256;
     const int64_t NT = (int64_t)N * T;
+    {
+    ProfScope ps(h, PH_PREP, s);
     prep_tokens_kernel<<<cdiv(NT, TB), TB, 0, s>>>(d_tokens, h->x_ids, h->y_ids, N, T, h->V, h->V);
     LAUNCH_COUNT(h);
-    {
         int cols8 = h->Ep / 8;
         gather_rows_f16_kernel<<<cdiv(NT * cols8, TB), TB, 0, s>>>(h->emb16, h->Ep, h->x_ids, h->xemb, h->Ep, NT, cols8);
         LAUNCH_COUNT(h);
@@ -215,8 +244,13 @@ static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, cudaStre
         const __half* in = li == 0 ? h->xemb : h->layers[li - 1].hs;
         const float* bias = h->params + l.b_off;
         // hoisted input contraction: pre[NT,4H] = in[NT,in] * Wx + b   (K3 in SURVEY §2.1)
-        int rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre, h->G4, 1.0f, bias), false, false, s);
+        int rc;
+        {
+            ProfScope ps(h, PH_INPUT_GEMM, s);
+            rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre, h->G4, 1.0f, bias), false, false, s);
+        }
         if (rc) return rc;
+        ProfScope ps_rec(h, PH_REC_FWD, s);
         if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
             tc_recurrent_supported(h->tc, N, H)) {
             rc = tc_lstm_forward(h->tc, h->pre, l.WhT16, l.gates, l.c, l.hs, N, T, H, h->Hp, h->G4p, s);
@@ -251,17 +285,20 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
     float* g_sb = h->grads ? h->grads + h->sb_off : nullptr;
     float* nll_out = d_nll_user ? d_nll_user : h->nll;
     const bool use_tc = !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) && tc_projection_supported(h->tc, H, h->V1);
+    if (train) FSMG_CUDA_OK(cudaMemsetAsync(h->dws_acc, 0, sizeof(float) * (size_t)H * h->Vp, s));
     for (int64_t r0 = 0; r0 < NT; r0 += h->chunk_rows) {
         int mc = (int)((NT - r0 < h->chunk_rows) ? NT - r0 : h->chunk_rows);
         const __half* hc = hs + r0 * h->Hp;
         int rc;
         if (use_tc) {
+            ProfScope ps(h, PH_PROJ_FWD, s);
             // fused: logits tile -> online (max,sumexp) partials + target logit; fp16 logits only when training
             rc = tc_projection_fwd(h->tc, hc, h->Hp, h->WsT16, h->Hp, sb, h->y_ids, r0, mc, N, T, H, h->V1,
-                                   train ? h->dlogits : nullptr, h->Vp, h->lse, nll_out, s);
-            h->launches += train ? 3 : 2;
+                                   train ? h->dlogits : nullptr, h->Vp, h->lse, nll_out, loss_scale, g_sb, s);
+            h->launches += 2;
             if (rc) return rc;
         } else {
+            ProfScope ps(h, PH_PROJ_FWD, s);
             rc = gemm_f16(h, mk(mc, h->V1, H, hc, h->Hp, h->WsT16, h->Hp, h->logits32, h->Vp, 1.0f, sb), false, false, s);
             if (rc) return rc;
             rowwise_nll_kernel<<<mc, 256, 0, s>>>(h->logits32, h->Vp, h->V1, h->y_ids, r0, N, T, h->lse, nll_out,
@@ -270,19 +307,29 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
             FSMG_LAUNCH_OK();
         }
         if (!train) continue;
-        // db_s += loss_scale * colsum(dlogits)
-        {
+        // db_s += loss_scale * colsum(dlogits)   (the tcgen05 route fuses this into its softmax-grad pass)
+        if (!use_tc) {
+            ProfScope ps(h, PH_SOFTMAX_GRAD, s);
             int rpb = 64;
             dim3 grid(cdiv(h->V1, 128), cdiv(mc, rpb));
             colsum_f16_kernel<<<grid, 128, 0, s>>>(h->dlogits, h->Vp, mc, h->V1, loss_scale, g_sb, rpb);
             LAUNCH_COUNT(h);
         }
         // dH[chunk] = dlogits * Ws^T   (unscaled; fp32)
-        rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H), false, false, s);
+        {
+            ProfScope ps(h, PH_DH, s);
+            rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H), false, false, s);
+        }
         if (rc) return rc;
         // dWs += loss_scale * hs_chunk^T * dlogits   (contraction over the chunk's tokens)
-        rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, g_sw, h->V1, loss_scale, nullptr, 0, 1, 0), true, true, s);
+        ProfScope ps_dws(h, PH_DWS, s);
+        rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 1, 0), true, true, s);
         if (rc) return rc;
+    }
+    if (train) {
+        int64_t total = (int64_t)H * h->V1;
+        unpad_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(h->dws_acc, h->Vp, g_sw, h->V1, H, h->V1);
+        LAUNCH_COUNT(h);
     }
     FSMG_LAUNCH_OK();
     return FSMG_OK;
@@ -300,6 +347,8 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
         int rc;
         bool persistent = !(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
                           tc_recurrent_supported(h->tc, N, H);
+        {
+        ProfScope ps_rec(h, PH_REC_BWD, s);
         if (persistent) {
             rc = tc_lstm_backward(h->tc, dh_all, Wh_rows, l.gates, l.c, h->dgates, N, T, H, h->G4p, s);
             LAUNCH_COUNT(h);
@@ -319,7 +368,9 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
             }
             FSMG_LAUNCH_OK();
         }
+        }
         // db = loss_scale * colsum(dgates)
+        ProfScope* ps_w = new ProfScope(h, PH_WGRAD, s);
         {
             int rpb = 256;
             dim3 grid(cdiv(h->G4, 128), cdiv(NT, rpb));
@@ -329,14 +380,16 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
         // dK[:in]  = loss_scale * in^T * dgates        (contraction over all tokens)
         float* gK = h->grads + l.k_off;
         rc = gemm_f16(h, mk(l.in, h->G4, (int)NT, in, l.inp, h->dgates, h->G4p, gK, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
-        if (rc) return rc;
+        if (rc) { delete ps_w; return rc; }
         // dK[in:]  = loss_scale * h_{t-1}^T * dgates_t  (tokens of steps 1..T-1; h_{-1} = 0)
         if (T > 1) {
             rc = gemm_f16(h, mk(H, h->G4, (int)(NT - N), l.hs, h->Hp, h->dgates + (int64_t)N * h->G4p, h->G4p,
                                 gK + (int64_t)l.in * h->G4, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
-            if (rc) return rc;
+            if (rc) { delete ps_w; return rc; }
         }
+        delete ps_w;
         // dInput[NT,in] = dgates * kernel[:in,:]^T
+        ProfScope ps_dx(h, PH_DX, s);
         float* dnext = h->dact[cur ^ 1];
         rc = gemm_f16(h, mk((int)NT, l.in, h->G4, h->dgates, h->G4p, l.K16, h->G4p, dnext, l.in), false, false, s);
         if (rc) return rc;
@@ -416,6 +469,7 @@ void fsmg_destroy(fsmg_handle* h) {
     if (!h) return;
     if (h->h_tok) cudaFreeHost(h->h_tok);
     if (h->h_scal) cudaFreeHost(h->h_scal);
+    for (auto ev : h->prof.pool) cudaEventDestroy(ev);
     delete h;
 }
 
@@ -429,6 +483,27 @@ int fsmg_param_info_at(const fsmg_handle* h, int index, fsmg_param_info* out) {
     return FSMG_OK;
 }
 int64_t fsmg_last_launch_count(const fsmg_handle* h) { return h ? h->launches : 0; }
+
+int fsmg_set_profile(fsmg_handle* h, int enable) {
+    if (!h) return set_error(FSMG_ERR_INVALID, "null handle");
+    h->prof.on = enable != 0;
+    return FSMG_OK;
+}
+int fsmg_read_profile(fsmg_handle* h, float* ms_out, int32_t* count_out, void* stream) {
+    if (!h || !ms_out) return set_error(FSMG_ERR_INVALID, "null argument");
+    FSMG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int i = 0; i < PH_COUNT; ++i) { ms_out[i] = 0.0f; if (count_out) count_out[i] = 0; }
+    for (auto& r : h->prof.recs) {
+        float ms = 0.0f;
+        FSMG_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+        ms_out[r.ph] += ms;
+        if (count_out) count_out[r.ph]++;
+    }
+    h->prof.recs.clear();
+    h->prof.used = 0;
+    return FSMG_OK;
+}
+const char* fsmg_profile_phase_name(int phase) { return (phase >= 0 && phase < PH_COUNT) ? kPhaseNames[phase] : ""; }
 
 int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, float* d_adam_v, void* d_workspace,
               int64_t workspace_bytes) {
@@ -497,6 +572,7 @@ int fsmg_apply_update(fsmg_handle* h, int64_t step, float* d_out_norm, void* str
     double t = (double)step + 1.0;
     double alpha = (double)lr_k * sqrt(1.0 - pow((double)h->cfg.beta2, t)) / (1.0 - pow((double)h->cfg.beta1, t));
     float* dense_sq = h->scalars + 8;
+    ProfScope ps(h, PH_UPDATE, s);
     FSMG_CUDA_OK(cudaMemsetAsync(dense_sq, 0, sizeof(float), s));
     sqnorm_f32_kernel<<<296, 256, 0, s>>>(h->grads, h->dense_begin, h->n_params, dense_sq);
     clip_adam_kernel<<<592, 256, 0, s>>>(h->params, h->grads, h->adam_m, h->adam_v, h->n_params, dense_sq,

@@ -395,6 +395,14 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, int64_t ld,
     }
 }
 
+// dst[r*ldd + c] = src[r*lds + c]  (drop the row padding of an accumulation buffer)
+__global__ void unpad_rows_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * cols) return;
+    int r = (int)(i / cols), c = (int)(i % cols);
+    dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

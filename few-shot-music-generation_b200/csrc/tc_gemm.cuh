@@ -267,53 +267,66 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     if (row_ok) {
                         const bool add_bias = ep.bias != nullptr && s_blk == 0;
                         const bool full = col0 + 32 <= sh.N;
+                        float v[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = ep.alpha * __uint_as_float(r[j]);
+                        if (add_bias) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < sh.N) ? ep.bias[col0 + j] : 0.0f;
+                        }
                         if (ep.c_half) {
                             __half* dst = reinterpret_cast<__half*>(ep.C) + (int64_t)row * ep.ldc + col0;
                             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
-                                    __half2 h[4];
+                                    __align__(16) __half2 h[4];
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) {
-                                        float v0 = ep.alpha * __uint_as_float(r[j + 2 * q]) + (add_bias ? ep.bias[col0 + j + 2 * q] : 0.0f);
-                                        float v1 = ep.alpha * __uint_as_float(r[j + 2 * q + 1]) + (add_bias ? ep.bias[col0 + j + 2 * q + 1] : 0.0f);
-                                        h[q] = __floats2half2_rn(v0, v1);
-                                    }
+                                    for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[j + 2 * q], v[j + 2 * q + 1]);
                                     *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(h);
                                 }
                             } else {
-                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j)
-                                    dst[j] = __float2half_rn(ep.alpha * __uint_as_float(r[j]) + (add_bias ? ep.bias[col0 + j] : 0.0f));
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < sh.N) dst[j] = __float2half_rn(v[j]);
                             }
                         } else {
                             float* dst = reinterpret_cast<float*>(ep.C) + (int64_t)row * ep.ldc + col0;
+                            const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
                             if (ep.atomic) {
-                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j)
-                                    atomicAdd(dst + j, ep.alpha * __uint_as_float(r[j]) + (add_bias ? ep.bias[col0 + j] : 0.0f));
-                            } else if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                                if (vec) {
 #pragma unroll
-                                for (int j = 0; j < 32; j += 4) {
-                                    float4 v;
-                                    v.x = ep.alpha * __uint_as_float(r[j]);
-                                    v.y = ep.alpha * __uint_as_float(r[j + 1]);
-                                    v.z = ep.alpha * __uint_as_float(r[j + 2]);
-                                    v.w = ep.alpha * __uint_as_float(r[j + 3]);
-                                    if (add_bias) {
-                                        const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
-                                        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                                    }
-                                    if (ep.accumulate) {
-                                        const float4 o = *reinterpret_cast<const float4*>(dst + j);
-                                        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-                                    }
-                                    *reinterpret_cast<float4*>(dst + j) = v;
+                                    for (int j = 0; j < 32; j += 4)
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                                                     "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (col0 + j < sh.N) atomicAdd(dst + j, v[j]);
                                 }
+                            } else if (vec) {
+                                if (ep.accumulate) {
+                                    float4 o[8];   // all loads in flight before the first dependent add/store
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) o[j] = __ldcg(reinterpret_cast<const float4*>(dst) + j);
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) {
+                                        v[4 * j] += o[j].x; v[4 * j + 1] += o[j].y; v[4 * j + 2] += o[j].z; v[4 * j + 3] += o[j].w;
+                                    }
+                                }
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                             } else {
-                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j) {
-                                    float v = ep.alpha * __uint_as_float(r[j]) + (add_bias ? ep.bias[col0 + j] : 0.0f);
-                                    if (ep.accumulate) v += dst[j];
-                                    dst[j] = v;
+                                if (ep.accumulate) {
+                                    float o[32];
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) o[j] = (col0 + j < sh.N) ? __ldcg(dst + j) : 0.0f;
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) v[j] += o[j];
                                 }
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < sh.N) dst[j] = v[j];
                             }
                         }
                     }
@@ -345,13 +358,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             if (col0 + 32 <= sh.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                                 for (int j = 0; j < 32; j += 8) {
-                                    __half2 h[4];
+                                    __align__(16) __half2 h[4];
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[j + 2 * q], v[j + 2 * q + 1]);
                                     *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(h);
                                 }
                             } else {
-                                for (int j = 0; j < 32 && col0 + j < sh.N; ++j) dst[j] = __float2half_rn(v[j]);
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < sh.N) dst[j] = __float2half_rn(v[j]);
                             }
                         }
                     }
@@ -400,6 +415,83 @@ __global__ void softmax_grad_inplace_kernel(__half* __restrict__ logits, int64_t
         float a = v < vp1 ? __expf(f.x - l) - (v == tgt ? 1.0f : 0.0f) : 0.0f;
         float b = v + 1 < vp1 ? __expf(f.y - l) - (v + 1 == tgt ? 1.0f : 0.0f) : 0.0f;
         *reinterpret_cast<__half2*>(row + v) = __floats2half2_rn(a, b);
+    }
+}
+
+
+// Fused post-pass over one L2-resident chunk of fp16 logits (training):
+//   (1) combine the per-(row, n-tile) (max, sumexp) partials -> lse ; nll = lse - target logit
+//   (2) in place: dlogits = exp(logit - lse) - onehot(y)            (unscaled, fp16)
+//   (3) db_s += alpha * column sums of dlogits                       (softmax_b gradient)
+// One CTA handles ROWS consecutive rows; each thread owns 8-column groups and keeps their column sums
+// in registers across the CTA's rows, so the bias gradient costs one atomicAdd per column per CTA.
+template <int ROWS, int THREADS, int MAXG>
+__global__ void __launch_bounds__(THREADS) softmax_grad_fused_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
+                                                                      const float2* __restrict__ part, int n_tiles,
+                                                                      const float* __restrict__ tgt, const int32_t* __restrict__ y,
+                                                                      int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
+                                                                      float* __restrict__ nll_out, float alpha, float* __restrict__ db) {
+    __shared__ float s_lse[ROWS];
+    __shared__ int s_tgt[ROWS];
+    const int r_begin = blockIdx.x * ROWS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int lr = warp; lr < ROWS; lr += THREADS / 32) {
+        const int row = r_begin + lr;
+        if (row >= rows) continue;
+        const float2* p = part + (int64_t)row * n_tiles;
+        float m = -INFINITY;
+        for (int i = lane; i < n_tiles; i += 32) m = fmaxf(m, p[i].x);
+        m = warp_max(m);
+        float s = 0.0f;
+        for (int i = lane; i < n_tiles; i += 32) s += p[i].y * __expf(p[i].x - m);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float lse = m + logf(s);
+            s_lse[lr] = lse;
+            const int64_t r = row0 + row;
+            s_tgt[lr] = y[r];
+            if (lse_out) lse_out[r] = lse;
+            const int t = (int)(r / N), n = (int)(r % N);
+            if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[row];
+        }
+    }
+    __syncthreads();
+    float csum[MAXG][8];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) csum[g][e] = 0.0f;
+    const int n_rows = min(ROWS, rows - r_begin);
+    for (int lr = 0; lr < n_rows; ++lr) {
+        __half* rowp = logits + (int64_t)(r_begin + lr) * ld;
+        const float lse = s_lse[lr];
+        const int tg = s_tgt[lr];
+#pragma unroll
+        for (int g = 0; g < MAXG; ++g) {
+            const int v0 = (g * THREADS + threadIdx.x) * 8;
+            if (v0 < ld) {
+                uint4 raw = *reinterpret_cast<const uint4*>(rowp + v0);
+                __half2* h2 = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2 f = __half22float2(h2[q]);
+                    const int v = v0 + 2 * q;
+                    float a = v < vp1 ? __expf(f.x - lse) - (v == tg ? 1.0f : 0.0f) : 0.0f;
+                    float b = v + 1 < vp1 ? __expf(f.y - lse) - (v + 1 == tg ? 1.0f : 0.0f) : 0.0f;
+                    h2[q] = __floats2half2_rn(a, b);
+                    csum[g][2 * q] += a;
+                    csum[g][2 * q + 1] += b;
+                }
+                *reinterpret_cast<uint4*>(rowp + v0) = raw;
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) {
+        const int v0 = (g * THREADS + threadIdx.x) * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (v0 + e < vp1) atomicAdd(db + v0 + e, alpha * csum[g][e]);
     }
 }
 
@@ -570,7 +662,7 @@ static inline bool tc_projection_supported(TcContext& c, int H, int V1) {
 
 static inline int tc_projection_fwd(TcContext& c, const __half* hc, int64_t ldh, const __half* WsT16, int64_t ldw, const float* sb,
                                     const int32_t* y, int64_t row0, int mc, int N, int T, int H, int V1, __half* logits16,
-                                    int64_t ld16, float* lse, float* nll_out, cudaStream_t s) {
+                                    int64_t ld16, float* lse, float* nll_out, float db_alpha, float* db, cudaStream_t s) {
     GemmArgs g;
     memset(&g, 0, sizeof g);
     g.M = mc; g.N = V1; g.K = H; g.A = hc; g.lda = ldh; g.B = WsT16; g.ldb = ldw;
@@ -585,8 +677,22 @@ static inline int tc_projection_fwd(TcContext& c, const __half* hc, int64_t ldh,
     if (rc) return rc;
     rc = tc_launch<tc::EPI_LSE>(c, p, ma, mb, false, ep, s);
     if (rc) return rc;
-    tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, p.sh.n_n, c.tgt, row0, mc, N, T, lse, nll_out);
-    if (logits16) tc::softmax_grad_inplace_kernel<<<mc, 256, 0, s>>>(logits16, ld16, V1, lse, y, row0);
+    if (!logits16) {
+        tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, p.sh.n_n, c.tgt, row0, mc, N, T, lse, nll_out);
+    } else {
+        constexpr int ROWS = 16, THREADS = 512;
+        const int groups = cdiv(ld16, THREADS * 8);
+        if (groups <= 3)
+            tc::softmax_grad_fused_kernel<ROWS, THREADS, 3><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, p.sh.n_n, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
+        else if (groups <= 8)
+            tc::softmax_grad_fused_kernel<ROWS, THREADS, 8><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, p.sh.n_n, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
+        else {
+            tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, p.sh.n_n, c.tgt, row0, mc, N, T, lse, nll_out);
+            tc::softmax_grad_inplace_kernel<<<mc, 256, 0, s>>>(logits16, ld16, V1, lse, y, row0);
+            dim3 grid(cdiv(V1, 128), cdiv(mc, 64));
+            colsum_f16_kernel<<<grid, 128, 0, s>>>(logits16, ld16, mc, V1, db_alpha, db, 64);
+        }
+    }
     FSMG_LAUNCH_OK();
     return 0;
 }

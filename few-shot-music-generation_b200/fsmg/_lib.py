@@ -15,6 +15,7 @@ FSMG_OK = 0
 FSMG_FLAG_SIMT_GEMM = 1
 FSMG_FLAG_SIMT_RECURRENT = 2
 FSMG_GRAD_EXTRA = 8
+FSMG_PROF_PHASES = 11
 
 
 class FsmgError(RuntimeError):
@@ -55,6 +56,9 @@ SYMBOLS = {
     "fsmg_eval_host": (C.c_int, [_P, _P, C.c_int32, C.POINTER(C.c_float), _P, _P]),
     "fsmg_train_host": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.POINTER(C.c_float), _P]),
     "fsmg_sample_host": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
+    "fsmg_set_profile": (C.c_int, [_P, C.c_int]),
+    "fsmg_read_profile": (C.c_int, [_P, _P, _P, _P]),
+    "fsmg_profile_phase_name": (C.c_char_p, [C.c_int]),
     "fsmg_last_launch_count": (C.c_int64, [_P]),
     "fsmg_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
 }

@@ -201,6 +201,17 @@ class Engine:
     def sample_host(self, n_songs: int, n_tokens: int) -> np.ndarray:
         return self.sample_greedy_device(n_songs, n_tokens).cpu().numpy()
 
+    def set_profile(self, enable: bool) -> None:
+        _lib.check(self.lib.fsmg_set_profile(self.h, int(enable)))
+
+    def read_profile(self) -> Dict[str, dict]:
+        """Per-phase device milliseconds (CUDA events on the engine's stream) since the last read."""
+        n = _lib.FSMG_PROF_PHASES
+        ms = (C.c_float * n)()
+        cnt = (C.c_int32 * n)()
+        _lib.check(self.lib.fsmg_read_profile(self.h, ms, cnt, self._stream()))
+        return {self.lib.fsmg_profile_phase_name(i).decode(): dict(ms=float(ms[i]), brackets=int(cnt[i])) for i in range(n)}
+
     def last_launch_count(self) -> int:
         return int(self.lib.fsmg_last_launch_count(self.h))
 

@@ -137,6 +137,14 @@ int fsmg_eval_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, floa
 int fsmg_train_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, int64_t step, float* h_mean_loss, void* stream);
 int fsmg_sample_host(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t* h_out, void* stream);
 
+/* Per-phase device timing for benchmarks: when enabled, every phase of forward_backward /
+ * apply_update is bracketed by CUDA events on the caller's stream.  fsmg_read_profile synchronises
+ * the stream, returns accumulated milliseconds and bracket counts per phase, and resets. */
+#define FSMG_PROF_PHASES 11
+int fsmg_set_profile(fsmg_handle* h, int enable);
+int fsmg_read_profile(fsmg_handle* h, float* ms_out, int32_t* count_out, void* stream);
+const char* fsmg_profile_phase_name(int phase);
+
 /* Introspection for benchmarks/tests: number of kernel launches issued by the last call,
  * and a GEMM self-test entry (C[M,N] = A[M,K] * B[N,K]^T, fp16 in, fp32 out) that drives the
  * tcgen05 core directly. */
