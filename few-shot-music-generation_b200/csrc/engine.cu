@@ -291,10 +291,19 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
         const __half* hc = hs + r0 * h->Hp;
         int rc;
         if (use_tc) {
-            ProfScope ps(h, PH_PROJ_FWD, s);
             // fused: logits tile -> online (max,sumexp) partials + target logit; fp16 logits only when training
-            rc = tc_projection_fwd(h->tc, hc, h->Hp, h->WsT16, h->Hp, sb, h->y_ids, r0, mc, N, T, H, h->V1,
-                                   train ? h->dlogits : nullptr, h->Vp, h->lse, nll_out, loss_scale, g_sb, s);
+            int n_part = 0;
+            {
+                ProfScope ps(h, PH_PROJ_FWD, s);
+                rc = tc_projection_gemm(h->tc, hc, h->Hp, h->WsT16, h->Hp, sb, h->y_ids, r0, mc, H, h->V1,
+                                        train ? h->dlogits : nullptr, h->Vp, &n_part, s);
+            }
+            if (rc) return rc;
+            {
+                ProfScope ps(h, PH_SOFTMAX_GRAD, s);
+                rc = tc_projection_post(h->tc, n_part, h->y_ids, r0, mc, N, T, h->V1, train ? h->dlogits : nullptr, h->Vp, h->lse,
+                                        nll_out, loss_scale, g_sb, s);
+            }
             h->launches += 2;
             if (rc) return rc;
         } else {

@@ -23,7 +23,9 @@ namespace tc {
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;                 // two epilogue warpgroups: each owns half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
+constexpr int EPI_STAGE_BYTES = 4096;            // per epilogue warp: 32 rows x 32 fp32 staging (swizzled)
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,6 +129,7 @@ struct EpiParams {
     void* C; int64_t ldc;
     const float* bias; float alpha;
     int c_half, accumulate, atomic;
+    int vec_ok;                         // host-checked: C base and ldc allow 16-byte (fp32) / 8-byte (fp16) row-chunk accesses
     // EPI_LSE: logits = acc + bias; per (row, n-tile) online (max, sumexp); target-logit pick; optional fp16 logits
     float2* part; int n_tiles_total;    // part[row * n_tiles_total + n_blk]
     const int32_t* y; int64_t row0;     // y[row0 + row]
@@ -148,7 +151,8 @@ struct SmemLayout {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 256) ? 4 : 6;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+    static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 template <int BN, int EPI, bool A_MN, bool B_MN>
@@ -158,7 +162,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+    uint8_t* epi_smem = smem + STAGES * L::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + L::EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -171,7 +176,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_slot, 2 * BN);   // 2 accumulator stages of BN fp32 columns
@@ -243,139 +248,174 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue warps (2..5): TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4; warpgroup (warp-2)/4 owns half of the columns =====
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int CHUNKS = BN / 64;                        // 32-column chunks per warp
+        float4* st4 = reinterpret_cast<float4*>(epi_smem + (warp - 2) * EPI_STAGE_BYTES);
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_blk = tile % sh.n_m, n_blk = (tile / sh.n_m) % sh.n_n, s_blk = tile / (sh.n_m * sh.n_n);
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int row = m_blk * BM + quad * 32 + lane;        // global row of this thread
+            const int row_w0 = m_blk * BM + quad * 32;            // first row of this warp
+            const int row = row_w0 + lane;                         // row held by this thread in TMEM
             const bool row_ok = row < sh.M;
             const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
             float run_max = -INFINITY, run_sum = 0.0f;
             int tgt_col = -1;
             if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - n_blk * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int cc = 0; cc < CHUNKS; ++cc) {
+                const int c = half * CHUNKS + cc;
                 uint32_t r[32];
                 tmem_ld32(t_row + c * 32, r);
                 tmem_ld_wait();
                 const int col0 = n_blk * BN + c * 32;
                 if (col0 >= sh.N) continue;   // warp-uniform
+                const bool full = col0 + 32 <= sh.N;
                 if (EPI == EPI_STORE) {
-                    if (row_ok) {
-                        const bool add_bias = ep.bias != nullptr && s_blk == 0;
-                        const bool full = col0 + 32 <= sh.N;
-                        float v[32];
+                    // phase 1: registers (one row per lane) -> swizzled smem (16-byte slot c8 ^ (row & 7))
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = ep.alpha * __uint_as_float(r[j]);
-                        if (add_bias) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] += (col0 + j < sh.N) ? ep.bias[col0 + j] : 0.0f;
+                    for (int c8 = 0; c8 < 8; ++c8)
+                        st4[lane * 8 + (c8 ^ (lane & 7))] =
+                            make_float4(ep.alpha * __uint_as_float(r[4 * c8]), ep.alpha * __uint_as_float(r[4 * c8 + 1]),
+                                        ep.alpha * __uint_as_float(r[4 * c8 + 2]), ep.alpha * __uint_as_float(r[4 * c8 + 3]));
+                    __syncwarp();
+                    // phase 2: 8 lanes cover one 128-byte row segment, 4 rows per instruction -> coalesced lines
+                    const int c8 = lane & 7;
+                    const int colv = col0 + 4 * c8;
+                    const bool add_bias = ep.bias != nullptr && s_blk == 0;
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (add_bias) {
+                        if (full) b4 = *reinterpret_cast<const float4*>(ep.bias + colv);   // bias vectors are 256-B aligned tensors
+                        else {
+                            b4.x = colv < sh.N ? ep.bias[colv] : 0.f; b4.y = colv + 1 < sh.N ? ep.bias[colv + 1] : 0.f;
+                            b4.z = colv + 2 < sh.N ? ep.bias[colv + 2] : 0.f; b4.w = colv + 3 < sh.N ? ep.bias[colv + 3] : 0.f;
                         }
-                        if (ep.c_half) {
-                            __half* dst = reinterpret_cast<__half*>(ep.C) + (int64_t)row * ep.ldc + col0;
-                            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+                    }
+                    const bool vec = full && ep.vec_ok;
+                    float4 v[8];
 #pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    __align__(16) __half2 h[4];
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = 4 * k + (lane >> 3);
+                        v[k] = st4[rr * 8 + (c8 ^ (rr & 7))];
+                        v[k].x += b4.x; v[k].y += b4.y; v[k].z += b4.z; v[k].w += b4.w;
+                    }
+                    if (ep.c_half) {
+                        __half* C = reinterpret_cast<__half*>(ep.C);
 #pragma unroll
-                                    for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[j + 2 * q], v[j + 2 * q + 1]);
-                                    *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(h);
-                                }
+                        for (int k = 0; k < 8; ++k) {
+                            const int grow = row_w0 + 4 * k + (lane >> 3);
+                            if (grow >= sh.M) continue;
+                            __half* dst = C + (int64_t)grow * ep.ldc + colv;
+                            if (vec) {
+                                __align__(8) __half2 hh[2] = {__floats2half2_rn(v[k].x, v[k].y), __floats2half2_rn(v[k].z, v[k].w)};
+                                *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hh);
                             } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < sh.N) dst[j] = __float2half_rn(v[j]);
+                                if (colv < sh.N) dst[0] = __float2half_rn(v[k].x);
+                                if (colv + 1 < sh.N) dst[1] = __float2half_rn(v[k].y);
+                                if (colv + 2 < sh.N) dst[2] = __float2half_rn(v[k].z);
+                                if (colv + 3 < sh.N) dst[3] = __float2half_rn(v[k].w);
                             }
-                        } else {
-                            float* dst = reinterpret_cast<float*>(ep.C) + (int64_t)row * ep.ldc + col0;
-                            const bool vec = full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-                            if (ep.atomic) {
-                                if (vec) {
+                        }
+                    } else {
+                        float* C = reinterpret_cast<float*>(ep.C);
+                        if (vec && ep.accumulate && !ep.atomic) {
+                            float4 o[8];   // all (coalesced) loads in flight before the first dependent add/store
 #pragma unroll
-                                    for (int j = 0; j < 32; j += 4)
-                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
-                                                     "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-                                } else {
+                            for (int k = 0; k < 8; ++k) {
+                                const int grow = row_w0 + 4 * k + (lane >> 3);
+                                o[k] = grow < sh.M ? __ldcg(reinterpret_cast<const float4*>(C + (int64_t)grow * ep.ldc + colv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
 #pragma unroll
-                                    for (int j = 0; j < 32; ++j)
-                                        if (col0 + j < sh.N) atomicAdd(dst + j, v[j]);
-                                }
-                            } else if (vec) {
-                                if (ep.accumulate) {
-                                    float4 o[8];   // all loads in flight before the first dependent add/store
+                            for (int k = 0; k < 8; ++k) { v[k].x += o[k].x; v[k].y += o[k].y; v[k].z += o[k].z; v[k].w += o[k].w; }
+                        }
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) o[j] = __ldcg(reinterpret_cast<const float4*>(dst) + j);
+                        for (int k = 0; k < 8; ++k) {
+                            const int grow = row_w0 + 4 * k + (lane >> 3);
+                            if (grow >= sh.M) continue;
+                            float* dst = C + (int64_t)grow * ep.ldc + colv;
+                            if (vec) {
+                                if (ep.atomic)
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
+                                else
+                                    *reinterpret_cast<float4*>(dst) = v[k];
+                            } else {
+                                const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-                                    for (int j = 0; j < 8; ++j) {
-                                        v[4 * j] += o[j].x; v[4 * j + 1] += o[j].y; v[4 * j + 2] += o[j].z; v[4 * j + 3] += o[j].w;
+                                for (int e = 0; e < 4; ++e) {
+                                    if (colv + e < sh.N) {
+                                        if (ep.atomic) atomicAdd(dst + e, e4[e]);
+                                        else if (ep.accumulate) dst[e] += e4[e];
+                                        else dst[e] = e4[e];
                                     }
                                 }
-#pragma unroll
-                                for (int j = 0; j < 32; j += 4)
-                                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            } else {
-                                if (ep.accumulate) {
-                                    float o[32];
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) o[j] = (col0 + j < sh.N) ? __ldcg(dst + j) : 0.0f;
-#pragma unroll
-                                    for (int j = 0; j < 32; ++j) v[j] += o[j];
-                                }
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < sh.N) dst[j] = v[j];
                             }
                         }
                     }
+                    __syncwarp();   // staging buffer is reused by the next chunk
                 } else {  // EPI_LSE
-                    if (row_ok) {
-                        float v[32];
-                        float cmax = -INFINITY;
+                    // bias for this chunk: one coalesced load, then broadcast by shuffle
+                    const float bl = (col0 + lane < sh.N) ? ep.bias[col0 + lane] : 0.0f;
+                    float v[32];
+                    float cmax = -INFINITY;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const bool ok = col0 + j < sh.N;
-                            v[j] = ok ? __uint_as_float(r[j]) + ep.bias[col0 + j] : -INFINITY;
-                            cmax = fmaxf(cmax, v[j]);
+                    for (int j = 0; j < 32; ++j) {
+                        const float bj = __shfl_sync(0xffffffffu, bl, j);
+                        v[j] = (col0 + j < sh.N) ? __uint_as_float(r[j]) + bj : -INFINITY;
+                        cmax = fmaxf(cmax, v[j]);
+                    }
+                    const int tj = tgt_col - c * 32;
+                    if (row_ok && tj >= 0 && tj < 32) {
+                        float tv = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) tv = (j == tj) ? v[j] : tv;
+                        ep.tgt[row] = tv;
+                    }
+                    const float nmax = fmaxf(run_max, cmax);
+                    float sacc = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sacc += __expf(v[j] - nmax);
+                    run_sum = run_sum * __expf(run_max - nmax) + sacc;
+                    run_max = nmax;
+                    if (ep.logits16) {
+                        // fp16 logits for the backward: staged through smem (64-B rows, slot c ^ ((row>>1)&3)) -> coalesced stores
+                        uint4* sh4 = reinterpret_cast<uint4*>(st4);
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            __align__(16) __half2 hh[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) hh[q] = __floats2half2_rn(v[8 * c4 + 2 * q], v[8 * c4 + 2 * q + 1]);
+                            sh4[lane * 4 + (c4 ^ ((lane >> 1) & 3))] = *reinterpret_cast<uint4*>(hh);
                         }
-                        const int tj = tgt_col - c * 32;
-                        if (tj >= 0 && tj < 32) {
-                            float tv = 0.0f;
+                        __syncwarp();
+                        const int c4 = lane & 3;
+                        const int colh = col0 + 8 * c4;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) tv = (j == tj) ? v[j] : tv;
-                            ep.tgt[row] = tv;
-                        }
-                        const float nmax = fmaxf(run_max, cmax);
-                        float s = 0.0f;
+                        for (int k = 0; k < 4; ++k) {
+                            const int rr = 8 * k + (lane >> 2);
+                            const int grow = row_w0 + rr;
+                            uint4 pk = sh4[rr * 4 + (c4 ^ ((rr >> 1) & 3))];
+                            if (grow < sh.M) {
+                                __half* dst = ep.logits16 + (int64_t)grow * ep.ld16 + colh;
+                                if (colh + 8 <= sh.N) *reinterpret_cast<uint4*>(dst) = pk;   // ld16 % 8 == 0, col0 % 32 == 0 -> 16-B aligned
+                                else {
+                                    const __half* ph = reinterpret_cast<const __half*>(&pk);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) s += __expf(v[j] - nmax);
-                        run_sum = run_sum * __expf(run_max - nmax) + s;
-                        run_max = nmax;
-                        if (ep.logits16) {
-                            __half* dst = ep.logits16 + (int64_t)row * ep.ld16 + col0;
-                            if (col0 + 32 <= sh.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                                for (int j = 0; j < 32; j += 8) {
-                                    __align__(16) __half2 h[4];
-#pragma unroll
-                                    for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(v[j + 2 * q], v[j + 2 * q + 1]);
-                                    *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<uint4*>(h);
+                                    for (int e = 0; e < 8; ++e)
+                                        if (colh + e < sh.N) dst[e] = ph[e];
                                 }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < sh.N) dst[j] = __float2half_rn(v[j]);
                             }
                         }
+                        __syncwarp();
                     }
                 }
             }
-            if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk] = make_float2(run_max, run_sum);
+            if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk * 2 + half] = make_float2(run_max, run_sum);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // 4 epilogue warps -> count 4
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // NUM_EPI_WARPS arrivals free the accumulator stage
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -518,7 +558,7 @@ struct TcContext {
 
 template <typename B>
 static inline void tc_carve(TcContext& c, B& b, int /*Nmax*/, int /*T*/, int V1, int /*Vp*/, int /*H*/, int chunk_rows) {
-    c.part_tiles = cdiv(V1, 128);
+    c.part_tiles = 2 * cdiv(V1, 128);   // two column halves per N tile
     c.part = b.template take<float2>((int64_t)chunk_rows * c.part_tiles);
     c.tgt = b.template take<float>(chunk_rows);
     c.counters = b.template take<int>(256);
@@ -643,6 +683,7 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
     memset(&ep, 0, sizeof ep);
     ep.C = g.C; ep.ldc = g.ldc; ep.bias = g.bias; ep.alpha = g.alpha; ep.c_half = g.c_half; ep.accumulate = g.accumulate;
     ep.atomic = g.atomic;
+    ep.vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc % 4) == 0) ? 1 : 0;
     if (p.sh.n_s > 1 && !g.atomic) {
         // plain store with split-K: zero the destination, then accumulate atomically
         FSMG_CUDA_OK(cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s));
@@ -660,9 +701,9 @@ static inline bool tc_projection_supported(TcContext& c, int H, int V1) {
     return c.ready && c.enabled && (H % 8 == 0 || true);
 }
 
-static inline int tc_projection_fwd(TcContext& c, const __half* hc, int64_t ldh, const __half* WsT16, int64_t ldw, const float* sb,
-                                    const int32_t* y, int64_t row0, int mc, int N, int T, int H, int V1, __half* logits16,
-                                    int64_t ld16, float* lse, float* nll_out, float db_alpha, float* db, cudaStream_t s) {
+static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh, const __half* WsT16, int64_t ldw, const float* sb,
+                                     const int32_t* y, int64_t row0, int mc, int H, int V1, __half* logits16, int64_t ld16,
+                                     int* n_part_out, cudaStream_t s) {
     GemmArgs g;
     memset(&g, 0, sizeof g);
     g.M = mc; g.N = V1; g.K = H; g.A = hc; g.lda = ldh; g.B = WsT16; g.ldb = ldw;
@@ -670,24 +711,30 @@ static inline int tc_projection_fwd(TcContext& c, const __half* hc, int64_t ldh,
     TcPlan p = tc_plan(c, mc, V1, H, false);
     tc::EpiParams ep;
     memset(&ep, 0, sizeof ep);
-    ep.bias = sb; ep.part = c.part; ep.n_tiles_total = p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
+    ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 2 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
     ep.logits16 = logits16; ep.ld16 = ld16;
+    *n_part_out = 2 * p.sh.n_n;
     CUtensorMap ma, mb;
     int rc = tc_make_maps(c, g, false, p.bn, &ma, &mb);
     if (rc) return rc;
-    rc = tc_launch<tc::EPI_LSE>(c, p, ma, mb, false, ep, s);
-    if (rc) return rc;
+    return tc_launch<tc::EPI_LSE>(c, p, ma, mb, false, ep, s);
+}
+
+// LSE combine (+ in-place softmax gradient and bias gradient when training) over the chunk
+static inline int tc_projection_post(TcContext& c, int n_part, const int32_t* y, int64_t row0, int mc, int N, int T, int V1,
+                                     __half* logits16, int64_t ld16, float* lse, float* nll_out, float db_alpha, float* db,
+                                     cudaStream_t s) {
     if (!logits16) {
-        tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, p.sh.n_n, c.tgt, row0, mc, N, T, lse, nll_out);
+        tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
     } else {
         constexpr int ROWS = 16, THREADS = 512;
         const int groups = cdiv(ld16, THREADS * 8);
         if (groups <= 3)
-            tc::softmax_grad_fused_kernel<ROWS, THREADS, 3><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, p.sh.n_n, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
+            tc::softmax_grad_fused_kernel<ROWS, THREADS, 3><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, n_part, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
         else if (groups <= 8)
-            tc::softmax_grad_fused_kernel<ROWS, THREADS, 8><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, p.sh.n_n, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
+            tc::softmax_grad_fused_kernel<ROWS, THREADS, 8><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, n_part, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
         else {
-            tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, p.sh.n_n, c.tgt, row0, mc, N, T, lse, nll_out);
+            tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
             tc::softmax_grad_inplace_kernel<<<mc, 256, 0, s>>>(logits16, ld16, V1, lse, y, row0);
             dim3 grid(cdiv(V1, 128), cdiv(mc, 64));
             colsum_f16_kernel<<<grid, 128, 0, s>>>(logits16, ld16, mc, V1, db_alpha, db, 64);

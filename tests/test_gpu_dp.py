@@ -1,0 +1,23 @@
+"""Multi-GPU data-parallel parity (needs >= 2 GPUs: `gpurun --gpus 2`): one process per GPU over
+NCCL; the sharded step must reproduce the oracle's single-process step on the union batch."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_two_gpu_data_parallel_step_matches_single_process(built_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    n = min(torch.cuda.device_count(), 8)
+    worker = Path(__file__).with_name("dp_worker.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+                          "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), str(worker)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "DP_OK" in out.stdout
