@@ -49,6 +49,26 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "memory");
 }
 
+// 32 lanes x 32 consecutive fp32 columns, registers -> TMEM
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 struct LstmParams {
     // forward
     const float* pre;      // [T*N, 4H] fp32: x_t * Wx + b (hoisted input contraction)
@@ -100,14 +120,16 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     uint64_t* empty_bar = bars + 8;             // [8]
     uint64_t* w_bar = bars + 16;
     uint64_t* tmem_full = bars + 17;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* pre_ready = bars + 18;            // epilogue has staged the next step's pre-activations in TMEM
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
     const int row_base = p.row_offset + g * p.rows_per_group;                       // first sequence of the group
     const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);     // sequences present (>= 1)
     int* counter = p.counters + g;
-    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL);
+    constexpr int BUF_COLS = MT * NCOL;               // one accumulator buffer; two buffers alternate per step
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BUF_COLS);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
@@ -115,6 +137,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
+        mbar_init(pre_ready, 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -150,9 +173,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             mbar_wait(w_bar, 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
+            uint32_t pr_phase = 0;
             for (int t = 1; t < p.T; ++t) {
-                // (TMEM reuse is safe: the loads of step t are only issued after this CTA's own epilogue of
-                //  step t-1 has drained the accumulators and published through the counter.)
+                // buffer t&1 already holds pre[t] (x_t*Wx + b), staged by the epilogue warps during step t-1:
+                // every MMA accumulates, so the epilogue reads finished gate pre-activations straight from TMEM
+                mbar_wait(pre_ready, pr_phase);
+                pr_phase ^= 1;
+                tc_fence_after();
+                const uint32_t d_buf = tmem_base + (uint32_t)((t & 1) * BUF_COLS);
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -164,7 +192,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
                             const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
-                            umma_f16(tmem_base + mt * NCOL, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_f16(d_buf + mt * NCOL, a_desc, b_desc, idesc, 1u);
                         }
                     }
                     umma_commit(&empty_bar[stage]);
@@ -182,15 +210,54 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 #pragma unroll
             for (int u = 0; u < U; ++u) c_state[mt][u] = 0.0f;
         uint32_t tf_phase = 0;
+        // stage pre[t] of this thread's rows into TMEM buffer (t & 1): 4 gates x U columns per row tile
+        auto stage_pre = [&](int t) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const int lrow = mt * 128 + quad * 32 + lane;
+                const bool ok = lrow < rows;
+                const float* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * (4 * p.H) + j * U;
+                const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (U == 32) {
+                        uint32_t rr[32];
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 a = ok ? __ldcs(reinterpret_cast<const float4*>(pre + q * p.H + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            rr[e] = __float_as_uint(a.x); rr[e + 1] = __float_as_uint(a.y); rr[e + 2] = __float_as_uint(a.z); rr[e + 3] = __float_as_uint(a.w);
+                        }
+                        tmem_st32(t_row + q * U, rr);
+                    } else {
+                        uint32_t rr[16];
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 a = ok ? __ldcs(reinterpret_cast<const float4*>(pre + q * p.H + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            rr[e] = __float_as_uint(a.x); rr[e + 1] = __float_as_uint(a.y); rr[e + 2] = __float_as_uint(a.z); rr[e + 3] = __float_as_uint(a.w);
+                        }
+                        tmem_st16(t_row + q * U, rr);
+                    }
+                }
+            }
+            tmem_st_wait();
+        };
+        stage_pre(0);
         for (int t = 0; t < p.T; ++t) {
-            if (t + 1 < p.T) {   // pull next step's pre-activation lines towards L2 while this step computes
+            if (t + 1 < p.T) {
+                // while the group exchanges h_t and the tensor core works on step t, stage step t+1's pre-activations
+                stage_pre(t + 1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pre_ready);
+                if (t + 2 < p.T) {   // and pull step t+2's lines towards L2
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                    const int lrow = mt * 128 + quad * 32 + lane;
-                    if (lrow < rows) {
-                        const float* nxt = p.pre + ((int64_t)(t + 1) * p.N + row_base + lrow) * (4 * p.H) + j * U;
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int lrow = mt * 128 + quad * 32 + lane;
+                        if (lrow < rows) {
+                            const float* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * (4 * p.H) + j * U;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
+                            for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
+                        }
                     }
                 }
             }
@@ -204,45 +271,29 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 const int lrow = mt * 128 + quad * 32 + lane;         // row inside the group
                 const bool ok = lrow < rows;
                 const int64_t r = (int64_t)t * p.N + row_base + lrow; // time-major token row
-                const float* pre = p.pre + r * (4 * p.H) + j * U;
                 __half* gout = p.gates + r * p.G4p + j * U;
-                const uint32_t t_row = tmem_base + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+                const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + mt * NCOL + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int u0 = 0; u0 < U; u0 += 8) {
                     float acc[4][8];
-                    if (t > 0) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t rr[8];
-                            tmem_ld8(t_row + q * U + u0, rr);
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t rr[8];
+                        tmem_ld8(t_row + q * U + u0, rr);
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) acc[q][e] = __uint_as_float(rr[e]);
-                        }
-                        tmem_ld_wait();
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) acc[q][e] = 0.0f;
+                        for (int e = 0; e < 8; ++e) acc[q][e] = __uint_as_float(rr[e]);
                     }
+                    tmem_ld_wait();
                     if (ok) {
-                        float pg[4][8];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float4 a = *reinterpret_cast<const float4*>(pre + q * p.H + u0);
-                            const float4 b = *reinterpret_cast<const float4*>(pre + q * p.H + u0 + 4);
-                            pg[q][0] = a.x; pg[q][1] = a.y; pg[q][2] = a.z; pg[q][3] = a.w;
-                            pg[q][4] = b.x; pg[q][5] = b.y; pg[q][6] = b.z; pg[q][7] = b.w;
-                        }
                         __align__(16) __half hq[4][8];
                         __align__(16) __half hh[8];
                         float cn[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float i_ = sigmoid_fast(pg[0][e] + acc[0][e]);
-                            const float j_ = tanh_fast(pg[1][e] + acc[1][e]);
-                            const float f_ = sigmoid_fast(pg[2][e] + acc[2][e] + 1.0f);   // forget_bias = 1 (A.2)
-                            const float o_ = sigmoid_fast(pg[3][e] + acc[3][e]);
+                            const float i_ = sigmoid_fast(acc[0][e]);
+                            const float j_ = tanh_fast(acc[1][e]);
+                            const float f_ = sigmoid_fast(acc[2][e] + 1.0f);   // forget_bias = 1 (A.2)
+                            const float o_ = sigmoid_fast(acc[3][e]);
                             const float cv = c_state[mt][u0 + e] * f_ + i_ * j_;
                             c_state[mt][u0 + e] = cv;
                             cn[e] = cv;
@@ -250,19 +301,20 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                             hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
                             hh[e] = __float2half_rn(tanh_fast(cv) * o_);
                         }
+                        // h first: it is what the other CTAs of the group are waiting for
+                        *reinterpret_cast<uint4*>(p.hs + r * p.Hp + j * U + u0) = *reinterpret_cast<uint4*>(hh);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(gout + q * p.H + u0) = *reinterpret_cast<uint4*>(hq[q]);
-                        *reinterpret_cast<uint4*>(p.hs + r * p.Hp + j * U + u0) = *reinterpret_cast<uint4*>(hh);
                         float* cdst = p.c + r * p.H + j * U + u0;
                         *reinterpret_cast<float4*>(cdst) = make_float4(cn[0], cn[1], cn[2], cn[3]);
                         *reinterpret_cast<float4*>(cdst + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
                     }
                 }
             }
+            // publish: CTA barrier, then ONE gpu-scope release (cumulative over the CTA's stores)
             tc_fence_before();
-            __threadfence();                      // this thread's h_t / stash stores are visible GPU-wide
             named_bar_sync(1, 128);
-            if (warp == 2 && lane == 0) red_release_add(counter, 1);
+            if (warp == 2 && lane == 0) { __threadfence(); red_release_add(counter, 1); }
         }
     }
     tc_fence_before();
@@ -371,6 +423,19 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         uint32_t tf_phase = 0;
         for (int s = 0; s < p.T; ++s) {
             const int t = p.T - 1 - s;
+            if (t > 0) {   // pull the next processed step's stash / upstream-gradient lines towards L2
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int lrow = mt * 128 + quad * 32 + lane;
+                    if (lrow < rows) {
+                        const int64_t rn = (int64_t)(t - 1) * p.N + row_base + lrow;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) prefetch_l2(p.gates + rn * p.G4p + q * p.H + j * U);
+                        prefetch_l2(p.dh_out + rn * p.H + j * U);
+                        prefetch_l2(p.c + rn * p.H + j * U);
+                    }
+                }
+            }
             if (s > 0) {
                 mbar_wait(tmem_full, tf_phase);
                 tf_phase ^= 1;
@@ -439,9 +504,8 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 }
             }
             tc_fence_before();
-            __threadfence();
             named_bar_sync(1, 128);
-            if (warp == 2 && lane == 0) red_release_add(counter, 1);
+            if (warp == 2 && lane == 0) { __threadfence(); red_release_add(counter, 1); }
         }
     }
     tc_fence_before();
