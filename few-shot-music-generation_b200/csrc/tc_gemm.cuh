@@ -102,6 +102,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for outstanding tcgen05.ld and tie the destination registers to the wait, so that no use of them can be
+// scheduled ahead of it (needed when loads are software-pipelined across chunks)
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
 // ---- descriptors ------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "SmemDescriptor": cute/arch/mma_sm100_desc.hpp):
@@ -256,8 +267,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int m_blk = tile % sh.n_m, n_blk = (tile / sh.n_m) % sh.n_n, s_blk = tile / (sh.n_m * sh.n_n);
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tc_fence_after();
             const int row_w0 = m_blk * BM + quad * 32;            // first row of this warp
             const int row = row_w0 + lane;                         // row held by this thread in TMEM
             const bool row_ok = row < sh.M;
@@ -265,12 +274,40 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float run_max = -INFINITY, run_sum = 0.0f;
             int tgt_col = -1;
             if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - n_blk * BN;
-#pragma unroll 1
+            // bias of every chunk of this tile, fetched before the accumulator is awaited (off the critical path)
+            float bias_lane[CHUNKS];
+#pragma unroll
+            for (int cc = 0; cc < CHUNKS; ++cc) {
+                const int colb = n_blk * BN + (half * CHUNKS + cc) * 32 + ((EPI == EPI_LSE) ? lane : 4 * (lane & 7));
+                bias_lane[cc] = 0.0f;
+                if (EPI == EPI_LSE) { if (colb < sh.N) bias_lane[cc] = ep.bias[colb]; }
+            }
+            float4 bias4[CHUNKS];
+            if (EPI == EPI_STORE) {
+                const bool add_bias = ep.bias != nullptr && s_blk == 0;
+#pragma unroll
+                for (int cc = 0; cc < CHUNKS; ++cc) {
+                    const int colv = n_blk * BN + (half * CHUNKS + cc) * 32 + 4 * (lane & 7);
+                    bias4[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (add_bias) {
+                        if (colv + 3 < sh.N) bias4[cc] = *reinterpret_cast<const float4*>(ep.bias + colv);   // bias tensors are 256-B aligned
+                        else {
+                            bias4[cc].x = colv < sh.N ? ep.bias[colv] : 0.f; bias4[cc].y = colv + 1 < sh.N ? ep.bias[colv + 1] : 0.f;
+                            bias4[cc].z = colv + 2 < sh.N ? ep.bias[colv + 2] : 0.f; bias4[cc].w = colv + 3 < sh.N ? ep.bias[colv + 3] : 0.f;
+                        }
+                    }
+                }
+            }
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tc_fence_after();
+            uint32_t rbuf[2][32];
+            tmem_ld32(t_row + (half * CHUNKS) * 32, rbuf[0]);
+#pragma unroll
             for (int cc = 0; cc < CHUNKS; ++cc) {
                 const int c = half * CHUNKS + cc;
-                uint32_t r[32];
-                tmem_ld32(t_row + c * 32, r);
-                tmem_ld_wait();
+                uint32_t (&r)[32] = rbuf[cc & 1];
+                tmem_ld_wait_dep(r);
+                if (cc + 1 < CHUNKS) tmem_ld32(t_row + (c + 1) * 32, rbuf[(cc + 1) & 1]);   // next chunk streams in while this one is processed
                 const int col0 = n_blk * BN + c * 32;
                 if (col0 >= sh.N) continue;   // warp-uniform
                 const bool full = col0 + 32 <= sh.N;
@@ -285,15 +322,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // phase 2: 8 lanes cover one 128-byte row segment, 4 rows per instruction -> coalesced lines
                     const int c8 = lane & 7;
                     const int colv = col0 + 4 * c8;
-                    const bool add_bias = ep.bias != nullptr && s_blk == 0;
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (add_bias) {
-                        if (full) b4 = *reinterpret_cast<const float4*>(ep.bias + colv);   // bias vectors are 256-B aligned tensors
-                        else {
-                            b4.x = colv < sh.N ? ep.bias[colv] : 0.f; b4.y = colv + 1 < sh.N ? ep.bias[colv + 1] : 0.f;
-                            b4.z = colv + 2 < sh.N ? ep.bias[colv + 2] : 0.f; b4.w = colv + 3 < sh.N ? ep.bias[colv + 3] : 0.f;
-                        }
-                    }
+                    const float4 b4 = bias4[cc];
                     const bool vec = full && ep.vec_ok;
                     float4 v[8];
 #pragma unroll
@@ -357,7 +386,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     __syncwarp();   // staging buffer is reused by the next chunk
                 } else {  // EPI_LSE
                     // bias for this chunk: one coalesced load, then broadcast by shuffle
-                    const float bl = (col0 + lane < sh.N) ? ep.bias[col0 + lane] : 0.0f;
+                    const float bl = bias_lane[cc];
                     float v[32];
                     float cmax = -INFINITY;
 #pragma unroll
@@ -502,27 +531,41 @@ __global__ void __launch_bounds__(THREADS) softmax_grad_fused_kernel(__half* __r
 #pragma unroll
         for (int e = 0; e < 8; ++e) csum[g][e] = 0.0f;
     const int n_rows = min(ROWS, rows - r_begin);
-    for (int lr = 0; lr < n_rows; ++lr) {
-        __half* rowp = logits + (int64_t)(r_begin + lr) * ld;
-        const float lse = s_lse[lr];
-        const int tg = s_tgt[lr];
+    constexpr int RB = (MAXG <= 3) ? 4 : 1;   // rows per batch: all loads of a batch are issued before the first exp (memory-level parallelism)
+    for (int lr0 = 0; lr0 < n_rows; lr0 += RB) {
+        uint4 raw[RB][MAXG];
 #pragma unroll
-        for (int g = 0; g < MAXG; ++g) {
-            const int v0 = (g * THREADS + threadIdx.x) * 8;
-            if (v0 < ld) {
-                uint4 raw = *reinterpret_cast<const uint4*>(rowp + v0);
-                __half2* h2 = reinterpret_cast<__half2*>(&raw);
+        for (int b = 0; b < RB; ++b) {
+            const __half* rowp = logits + (int64_t)(r_begin + lr0 + b) * ld;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float2 f = __half22float2(h2[q]);
-                    const int v = v0 + 2 * q;
-                    float a = v < vp1 ? __expf(f.x - lse) - (v == tg ? 1.0f : 0.0f) : 0.0f;
-                    float b = v + 1 < vp1 ? __expf(f.y - lse) - (v + 1 == tg ? 1.0f : 0.0f) : 0.0f;
-                    h2[q] = __floats2half2_rn(a, b);
-                    csum[g][2 * q] += a;
-                    csum[g][2 * q + 1] += b;
+            for (int g = 0; g < MAXG; ++g) {
+                const int v0 = (g * THREADS + threadIdx.x) * 8;
+                if (lr0 + b < n_rows && v0 < ld) raw[b][g] = __ldcg(reinterpret_cast<const uint4*>(rowp + v0));
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            if (lr0 + b >= n_rows) break;
+            __half* rowp = logits + (int64_t)(r_begin + lr0 + b) * ld;
+            const float lse = s_lse[lr0 + b];
+            const int tg = s_tgt[lr0 + b];
+#pragma unroll
+            for (int g = 0; g < MAXG; ++g) {
+                const int v0 = (g * THREADS + threadIdx.x) * 8;
+                if (v0 < ld) {
+                    __half2* h2 = reinterpret_cast<__half2*>(&raw[b][g]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 f = __half22float2(h2[q]);
+                        const int v = v0 + 2 * q;
+                        float a = v < vp1 ? __expf(f.x - lse) - (v == tg ? 1.0f : 0.0f) : 0.0f;
+                        float bb = v + 1 < vp1 ? __expf(f.y - lse) - (v + 1 == tg ? 1.0f : 0.0f) : 0.0f;
+                        h2[q] = __floats2half2_rn(a, bb);
+                        csum[g][2 * q] += a;
+                        csum[g][2 * q + 1] += bb;
+                    }
+                    *reinterpret_cast<uint4*>(rowp + v0) = raw[b][g];
                 }
-                *reinterpret_cast<uint4*>(rowp + v0) = raw;
             }
         }
     }

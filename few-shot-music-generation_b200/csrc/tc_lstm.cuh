@@ -120,8 +120,10 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     uint64_t* empty_bar = bars + 8;             // [8]
     uint64_t* w_bar = bars + 16;
     uint64_t* tmem_full = bars + 17;
-    uint64_t* pre_ready = bars + 18;            // epilogue has staged the next step's pre-activations in TMEM
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+    uint64_t* pre_ready = bars + 18;            // [2] one per TMEM buffer: "pre-activations of the step that uses this buffer are staged".
+                                                // Two barriers (not one) so the epilogue can never run two phases ahead of the MMA
+                                                // thread (e.g. while it still waits for the one-time weight load).
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
@@ -137,7 +139,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
-        mbar_init(pre_ready, 4);
+        mbar_init(&pre_ready[0], 4);
+        mbar_init(&pre_ready[1], 4);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -173,12 +176,12 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             mbar_wait(w_bar, 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
-            uint32_t pr_phase = 0;
+            uint32_t pr_phase[2] = {0, 0};
             for (int t = 1; t < p.T; ++t) {
                 // buffer t&1 already holds pre[t] (x_t*Wx + b), staged by the epilogue warps during step t-1:
                 // every MMA accumulates, so the epilogue reads finished gate pre-activations straight from TMEM
-                mbar_wait(pre_ready, pr_phase);
-                pr_phase ^= 1;
+                mbar_wait(&pre_ready[t & 1], pr_phase[t & 1]);
+                pr_phase[t & 1] ^= 1;
                 tc_fence_after();
                 const uint32_t d_buf = tmem_base + (uint32_t)((t & 1) * BUF_COLS);
                 for (int kc = 0; kc < KC; ++kc) {
@@ -248,7 +251,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 stage_pre(t + 1);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(pre_ready);
+                if (lane == 0) mbar_arrive(&pre_ready[(t + 1) & 1]);
                 if (t + 2 < p.T) {   // and pull step t+2's lines towards L2
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
