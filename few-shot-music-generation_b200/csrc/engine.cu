@@ -88,6 +88,12 @@ struct fsmg_handle {
     float *s_x = nullptr, *s_g = nullptr, *s_logits = nullptr;
     std::vector<float*> s_c, s_h;
     int chunk_rows = 0;
+    // projection backward overlap: dH / dWs GEMMs of chunk i run on two auxiliary streams while the logits GEMM of
+    // chunk i+1 runs on the caller's stream (double-buffered dlogits); fills the tail waves of the persistent GEMMs
+    __half* dlogits_b[2] = {nullptr, nullptr};
+    cudaStream_t aux[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_dh[2] = {nullptr, nullptr}, ev_dws[2] = {nullptr, nullptr};
+    int overlap = 1;
     int samp_max = 0;
     // pinned host staging
     int32_t* h_tok = nullptr;
@@ -154,13 +160,19 @@ static void carve(fsmg_handle* h, char* base) {
         l.hs = b.take<__half>(NT * h->Hp);
     }
     // projection chunk: rows sized so the fp16 logits chunk stays L2-resident (<= ~48 MB)
-    int64_t rows = (48ll << 20) / ((int64_t)h->Vp * 2);
+    const char* env_mb = getenv("FSMG_CHUNK_MB");
+    const char* env_ov = getenv("FSMG_OVERLAP");
+    h->overlap = env_ov ? atoi(env_ov) : 1;
+    const int64_t chunk_mb = env_mb ? atoi(env_mb) : (h->overlap ? 32 : 48);   // two chunks are in flight when overlapping
+    int64_t rows = (chunk_mb << 20) / ((int64_t)h->Vp * 2);
     rows = rows / 128 * 128;
     if (rows < 128) rows = 128;
     if (rows > NT) rows = round_up(NT, 128);
     h->chunk_rows = (int)rows;
     h->logits32 = b.take<float>(rows * h->Vp);
     h->dlogits = b.take<__half>(rows * h->Vp);
+    h->dlogits_b[0] = h->dlogits;
+    h->dlogits_b[1] = b.take<__half>(rows * h->Vp);
     h->dws_acc = b.take<float>((int64_t)h->H * h->Vp);   // dWs accumulated with 16-byte aligned rows (V' is odd)
     // sampler (fp32 route)
     h->samp_max = h->Nmax;
@@ -286,9 +298,19 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
     float* nll_out = d_nll_user ? d_nll_user : h->nll;
     const bool use_tc = !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) && tc_projection_supported(h->tc, H, h->V1);
     if (train) FSMG_CUDA_OK(cudaMemsetAsync(h->dws_acc, 0, sizeof(float) * (size_t)H * h->Vp, s));
-    for (int64_t r0 = 0; r0 < NT; r0 += h->chunk_rows) {
+    // overlap is switched off while profiling so that per-phase event brackets do not double count
+    const bool overlap = train && use_tc && h->overlap && !h->prof.on && h->aux[0] != nullptr;
+    int64_t chunk_idx = 0;
+    for (int64_t r0 = 0; r0 < NT; r0 += h->chunk_rows, ++chunk_idx) {
         int mc = (int)((NT - r0 < h->chunk_rows) ? NT - r0 : h->chunk_rows);
         const __half* hc = hs + r0 * h->Hp;
+        const int buf = overlap ? (int)(chunk_idx & 1) : 0;
+        h->dlogits = h->dlogits_b[buf];
+        cudaStream_t s_dh = overlap ? h->aux[0] : s, s_dws = overlap ? h->aux[1] : s;
+        if (overlap && chunk_idx >= 2) {   // the buffer is free once both consumers of chunk i-2 are done
+            FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dh[buf], 0));
+            FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dws[buf], 0));
+        }
         int rc;
         if (use_tc) {
             // fused: logits tile -> online (max,sumexp) partials + target logit; fp16 logits only when training
@@ -324,17 +346,35 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
             colsum_f16_kernel<<<grid, 128, 0, s>>>(h->dlogits, h->Vp, mc, h->V1, loss_scale, g_sb, rpb);
             LAUNCH_COUNT(h);
         }
+        if (overlap) {
+            FSMG_CUDA_OK(cudaEventRecord(h->ev_ready[buf], s));
+            FSMG_CUDA_OK(cudaStreamWaitEvent(s_dh, h->ev_ready[buf], 0));
+            FSMG_CUDA_OK(cudaStreamWaitEvent(s_dws, h->ev_ready[buf], 0));
+        }
         // dH[chunk] = dlogits * Ws^T   (unscaled; fp32)
         {
-            ProfScope ps(h, PH_DH, s);
-            rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H), false, false, s);
+            ProfScope ps(h, PH_DH, s_dh);
+            rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H), false, false, s_dh);
         }
         if (rc) return rc;
         // dWs += loss_scale * hs_chunk^T * dlogits   (contraction over the chunk's tokens)
-        ProfScope ps_dws(h, PH_DWS, s);
-        rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 1, 0), true, true, s);
+        {
+            ProfScope ps_dws(h, PH_DWS, s_dws);
+            rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 1, 0), true, true, s_dws);
+        }
         if (rc) return rc;
+        if (overlap) {
+            FSMG_CUDA_OK(cudaEventRecord(h->ev_dh[buf], s_dh));
+            FSMG_CUDA_OK(cudaEventRecord(h->ev_dws[buf], s_dws));
+        }
     }
+    if (overlap) {   // join: everything after the projection (BPTT) is ordered behind both auxiliary streams
+        for (int b2 = 0; b2 < 2 && b2 < chunk_idx; ++b2) {
+            FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dh[b2], 0));
+            FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dws[b2], 0));
+        }
+    }
+    h->dlogits = h->dlogits_b[0];
     if (train) {
         int64_t total = (int64_t)H * h->V1;
         unpad_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(h->dws_acc, h->Vp, g_sw, h->V1, H, h->V1);
@@ -479,6 +519,12 @@ void fsmg_destroy(fsmg_handle* h) {
     if (h->h_tok) cudaFreeHost(h->h_tok);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (auto ev : h->prof.pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
+        if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
+        if (h->ev_dh[i]) cudaEventDestroy(h->ev_dh[i]);
+        if (h->ev_dws[i]) cudaEventDestroy(h->ev_dws[i]);
+    }
     delete h;
 }
 
@@ -526,6 +572,14 @@ int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, 
     carve(h, h->ws);
     int rc = tc_init(h->tc);
     if (rc) return rc;
+    if (!h->aux[0]) {
+        for (int i = 0; i < 2; ++i) {
+            FSMG_CUDA_OK(cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking));
+            FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_ready[i], cudaEventDisableTiming));
+            FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dh[i], cudaEventDisableTiming));
+            FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dws[i], cudaEventDisableTiming));
+        }
+    }
     h->bound = true;
     return FSMG_OK;
 }

@@ -60,6 +60,24 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// multicast variant: the box lands at the same smem offset of every CTA in `mask`, and each destination CTA's
+// mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -87,6 +105,13 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (a smem stage fed by multicast is free only
+// when all CTAs that received the data have consumed it)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -151,6 +176,7 @@ struct EpiParams {
 struct GemmShape {
     int M, N, K;
     int n_m, n_n, n_s;      // tiles along M, N and K-splits
+    int n_mp;               // M tiles per cluster-tile row = ceil(n_m / CL): a cluster of CL CTAs owns CL consecutive M tiles of one N tile
     int kb_per_split;       // k-blocks per split
     int kb_total;
 };
@@ -166,7 +192,10 @@ struct SmemLayout {
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-template <int BN, int EPI, bool A_MN, bool B_MN>
+// CL = 2: thread-block cluster of two CTAs working on two vertically adjacent output tiles (same N tile).  Each CTA
+// fetches HALF of the shared B tile and TMA-multicasts it to both, cutting the L2->SMEM operand traffic by a third
+// (the K-streaming mainloop of a 128 x 256 tile is L2-bandwidth bound: 96 B/clk/SM at full tensor rate).
+template <int BN, int EPI, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape sh, EpiParams ep) {
     using L = SmemLayout<BN>;
@@ -181,18 +210,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = sh.n_m * sh.n_n * sh.n_s;
+    const int total_tiles = sh.n_mp * sh.n_n * sh.n_s;          // cluster-tiles
+    const int cta_rank = (CL == 2) ? (int)cluster_ctarank() : 0;
+    const int first_tile = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_stride = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_base_slot, 2 * BN);   // 2 accumulator stages of BN fp32 columns
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();      // peer barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -200,8 +233,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m_blk = tile % sh.n_m, n_blk = (tile / sh.n_m) % sh.n_n, s_blk = tile / (sh.n_m * sh.n_n);
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+                const int m_blk = (tile % sh.n_mp) * CL + cta_rank, n_blk = (tile / sh.n_mp) % sh.n_n, s_blk = tile / (sh.n_mp * sh.n_n);
                 const int kb0 = s_blk * sh.kb_per_split;
                 const int kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -215,11 +248,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     } else {
                         tma_load_2d(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
                     }
-                    if (B_MN) {
+                    if (CL == 1) {
+                        if (B_MN) {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &map_b, n_blk * BN + j * 64, kb * BK, &full_bar[stage]);
-                    } else {
-                        tma_load_2d(sb, &map_b, kb * BK, n_blk * BN, &full_bar[stage]);
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &map_b, n_blk * BN + j * 64, kb * BK, &full_bar[stage]);
+                        } else {
+                            tma_load_2d(sb, &map_b, kb * BK, n_blk * BN, &full_bar[stage]);
+                        }
+                    } else {   // this CTA fetches its half of the B tile and multicasts it to both CTAs of the cluster
+                        if (B_MN) {
+#pragma unroll
+                            for (int jj = 0; jj < BN / 128; ++jj) {
+                                const int j = cta_rank * (BN / 128) + jj;
+                                tma_load_2d_mc(sb + j * 8192, &map_b, n_blk * BN + j * 64, kb * BK, &full_bar[stage], (uint16_t)0x3);
+                            }
+                        } else {
+                            tma_load_2d_mc(sb + cta_rank * (BN / 2) * 128, &map_b, kb * BK, n_blk * BN + cta_rank * (BN / 2), &full_bar[stage], (uint16_t)0x3);
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -231,8 +276,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int s_blk = tile / (sh.n_m * sh.n_n);
+            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+                const int s_blk = tile / (sh.n_mp * sh.n_n);
                 const int kb0 = s_blk * sh.kb_per_split;
                 const int kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -251,7 +296,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
                         umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
+                    if (CL == 2) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' producers write into both CTAs' stage
+                    else umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
@@ -265,8 +311,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr int CHUNKS = BN / 64;                        // 32-column chunks per warp
         float4* st4 = reinterpret_cast<float4*>(epi_smem + (warp - 2) * EPI_STAGE_BYTES);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int m_blk = tile % sh.n_m, n_blk = (tile / sh.n_m) % sh.n_n, s_blk = tile / (sh.n_m * sh.n_n);
+        for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+            const int m_blk = (tile % sh.n_mp) * CL + cta_rank, n_blk = (tile / sh.n_mp) % sh.n_n, s_blk = tile / (sh.n_mp * sh.n_n);
             const int row_w0 = m_blk * BM + quad * 32;            // first row of this warp
             const int row = row_w0 + lane;                         // row held by this thread in TMEM
             const bool row_ok = row < sh.M;
@@ -450,6 +496,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();      // no CTA exits while its peer may still multicast into it / signal its barriers
     if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
@@ -597,6 +644,7 @@ struct TcContext {
     int part_tiles = 0;
     int* counters = nullptr;   // [256] group-progress counters of the persistent recurrent kernels
     int enabled = 1;
+    int cluster = 2;           // CTAs per cluster of the GEMM core (2 = B-tile multicast pairs, 1 = no clusters)
 };
 
 template <typename B>
@@ -611,6 +659,8 @@ static inline int tc_init(TcContext& c) {
     if (c.ready) return 0;
     const char* env = getenv("FSMG_TC");
     c.enabled = env ? atoi(env) : 1;
+    const char* envc = getenv("FSMG_CLUSTER");
+    c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
     int dev = 0;
     FSMG_CUDA_OK(cudaGetDevice(&dev));
     FSMG_CUDA_OK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -619,8 +669,10 @@ static inline int tc_init(TcContext& c) {
     FSMG_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) return set_error(-2, "cuTensorMapEncodeTiled not available from the driver");
     c.encode = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
-#define FSMG_SET_SMEM(BN, EPI, AM, BMN)                                                                               \
-    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define FSMG_SET_SMEM(BN, EPI, AM, BMN)                                                                                  \
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      tc::SmemLayout<BN>::TOTAL));                                                       \
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       tc::SmemLayout<BN>::TOTAL))
     FSMG_SET_SMEM(256, tc::EPI_STORE, false, false);
     FSMG_SET_SMEM(256, tc::EPI_STORE, true, true);
@@ -664,6 +716,7 @@ struct TcPlan {
     int bn;
     tc::GemmShape sh;
     int grid;
+    int cl;   // cluster size (1 or 2)
 };
 
 static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split) {
@@ -674,10 +727,13 @@ static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow
     sh.n_m = cdiv(M, tc::BM);
     sh.n_n = cdiv(N, p.bn);
     sh.kb_total = cdiv(K, tc::BK);
-    int tiles = sh.n_m * sh.n_n;
+    p.cl = (c.cluster == 2 && sh.n_m >= 2) ? 2 : 1;     // pairs need two M tiles that share a B tile
+    sh.n_mp = cdiv(sh.n_m, p.cl);
+    const int slots = c.num_sms / p.cl;                  // concurrently resident clusters
+    int tiles = sh.n_mp * sh.n_n;                        // cluster-tiles
     int split = 1;
-    if (allow_split && tiles < c.num_sms) {
-        split = c.num_sms / tiles;                       // fill the machine once
+    if (allow_split && tiles < slots) {
+        split = slots / tiles;                           // fill the machine once
         int max_split = sh.kb_total / 8;                 // keep >= 8 k-blocks (512 k) per slice
         if (split > max_split) split = max_split;
         if (split < 1) split = 1;
@@ -685,31 +741,52 @@ static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow
     sh.kb_per_split = cdiv(sh.kb_total, split);
     sh.n_s = cdiv(sh.kb_total, sh.kb_per_split);
     int total = tiles * sh.n_s;
-    p.grid = total < c.num_sms ? total : c.num_sms;
+    p.grid = (total < slots ? total : slots) * p.cl;
     return p;
+}
+
+template <typename K>
+static inline int tc_launch_kernel(K kernel, const TcPlan& p, int smem, const CUtensorMap& ma, const CUtensorMap& mb,
+                                   const tc::EpiParams& ep, cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(p.grid);
+    cfg.blockDim = dim3(tc::NUM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = p.cl > 1 ? 1 : 0;
+    FSMG_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, ma, mb, p.sh, ep));
+    return 0;
 }
 
 template <int EPI>
 static inline int tc_launch(const TcContext& c, const TcPlan& p, const CUtensorMap& ma, const CUtensorMap& mb, bool mn,
                             const tc::EpiParams& ep, cudaStream_t s) {
 #define FSMG_GO(BN, MN)                                                                                                   \
-    tc::tc_gemm_kernel<BN, EPI, MN, MN><<<p.grid, tc::NUM_THREADS, tc::SmemLayout<BN>::TOTAL, s>>>(ma, mb, p.sh, ep)
+    (p.cl == 2 ? tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 2>, p, tc::SmemLayout<BN>::TOTAL, ma, mb, ep, s)       \
+               : tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 1>, p, tc::SmemLayout<BN>::TOTAL, ma, mb, ep, s))
+    int rc = 0;
     if constexpr (EPI == tc::EPI_LSE) {
-        if (p.bn == 256) FSMG_GO(256, false); else FSMG_GO(128, false);
+        rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
     } else {
-        if (!mn) { if (p.bn == 256) FSMG_GO(256, false); else FSMG_GO(128, false); }
-        else { if (p.bn == 256) FSMG_GO(256, true); else FSMG_GO(128, true); }
+        if (!mn) rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
+        else rc = (p.bn == 256) ? FSMG_GO(256, true) : FSMG_GO(128, true);
     }
 #undef FSMG_GO
+    if (rc) return rc;
     FSMG_LAUNCH_OK();
     return 0;
 }
 
-static inline int tc_make_maps(const TcContext& c, const GemmArgs& g, bool mn, int bn, CUtensorMap* ma, CUtensorMap* mb) {
+static inline int tc_make_maps(const TcContext& c, const GemmArgs& g, bool mn, int bn, int cl, CUtensorMap* ma, CUtensorMap* mb) {
     int rc;
     if (!mn) {
         if ((rc = make_map_f16(c, ma, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, tc::BK, tc::BM))) return rc;
-        if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, tc::BK, (uint32_t)bn))) return rc;
+        if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, tc::BK, (uint32_t)(bn / cl)))) return rc;   // each CTA of a pair fetches half of B
     } else {
         if ((rc = make_map_f16(c, ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 64, tc::BK))) return rc;
         if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 64, tc::BK))) return rc;
@@ -733,7 +810,7 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
         ep.atomic = 1;
     }
     CUtensorMap ma, mb;
-    int rc = tc_make_maps(c, g, a_mn, p.bn, &ma, &mb);
+    int rc = tc_make_maps(c, g, a_mn, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;
     return tc_launch<tc::EPI_STORE>(c, p, ma, mb, a_mn, ep, s);
 }
@@ -758,7 +835,7 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     ep.logits16 = logits16; ep.ld16 = ld16;
     *n_part_out = 2 * p.sh.n_n;
     CUtensorMap ma, mb;
-    int rc = tc_make_maps(c, g, false, p.bn, &ma, &mb);
+    int rc = tc_make_maps(c, g, false, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;
     return tc_launch<tc::EPI_LSE>(c, p, ma, mb, false, ep, s);
 }
