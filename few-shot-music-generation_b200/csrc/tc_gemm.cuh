@@ -625,6 +625,81 @@ __global__ void __launch_bounds__(THREADS) softmax_grad_fused_kernel(__half* __r
     }
 }
 
+
+// Strip version of the fused post-pass (default): a CTA of 128 threads owns a strip of ROWS rows x 1024 columns; each
+// thread owns 8 fixed columns and walks down the strip with 8 rows of 16-byte loads in flight, so column sums stay
+// in 8 registers and the kernel needs ~50 registers and 256 B of smem: it can share an SM with a GEMM CTA, and
+// there are enough small CTAs (cols/1024 x rows/ROWS) to keep >80 KB per SM in flight.
+template <int ROWS>
+__global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
+                                                                 const float2* __restrict__ part, int n_tiles,
+                                                                 const float* __restrict__ tgt, const int32_t* __restrict__ y,
+                                                                 int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
+                                                                 float* __restrict__ nll_out, float alpha, float* __restrict__ db) {
+    __shared__ float s_lse[ROWS];
+    __shared__ int s_tgt[ROWS];
+    const int r_begin = blockIdx.y * ROWS;
+    const int n_rows = min(ROWS, rows - r_begin);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int lr = warp; lr < n_rows; lr += 4) {
+        const int row = r_begin + lr;
+        const float2* p = part + (int64_t)row * n_tiles;
+        float m = -INFINITY;
+        for (int i = lane; i < n_tiles; i += 32) m = fmaxf(m, p[i].x);
+        m = warp_max(m);
+        float s = 0.0f;
+        for (int i = lane; i < n_tiles; i += 32) s += p[i].y * __expf(p[i].x - m);
+        s = warp_sum(s);
+        if (lane == 0) {
+            const float lse = m + logf(s);
+            const int64_t r = row0 + row;
+            s_lse[lr] = lse;
+            s_tgt[lr] = y[r];
+            if (blockIdx.x == 0) {
+                if (lse_out) lse_out[r] = lse;
+                const int t = (int)(r / N), n = (int)(r % N);
+                if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[row];
+            }
+        }
+    }
+    __syncthreads();
+    const int v0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (v0 >= ld) return;
+    float csum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) csum[e] = 0.0f;
+    __half* base = logits + (int64_t)r_begin * ld + v0;
+    constexpr int RB = 8;
+    for (int lr0 = 0; lr0 < n_rows; lr0 += RB) {
+        uint4 raw[RB];
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+            if (lr0 + b < n_rows) raw[b] = __ldcg(reinterpret_cast<const uint4*>(base + (int64_t)(lr0 + b) * ld));
+#pragma unroll
+        for (int b = 0; b < RB; ++b) {
+            if (lr0 + b < n_rows) {
+                const float lse = s_lse[lr0 + b];
+                const int tg = s_tgt[lr0 + b] - v0;
+                __half2* h2 = reinterpret_cast<__half2*>(&raw[b]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 f = __half22float2(h2[q]);
+                    const int v = v0 + 2 * q;
+                    const float a = v < vp1 ? __expf(f.x - lse) - (2 * q == tg ? 1.0f : 0.0f) : 0.0f;
+                    const float bb = v + 1 < vp1 ? __expf(f.y - lse) - (2 * q + 1 == tg ? 1.0f : 0.0f) : 0.0f;
+                    h2[q] = __floats2half2_rn(a, bb);
+                    csum[2 * q] += a;
+                    csum[2 * q + 1] += bb;
+                }
+                *reinterpret_cast<uint4*>(base + (int64_t)(lr0 + b) * ld) = raw[b];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (v0 + e < vp1) atomicAdd(db + v0 + e, alpha * csum[e]);
+}
+
 }  // namespace tc
 
 // =====================================================================================================
@@ -645,6 +720,7 @@ struct TcContext {
     int* counters = nullptr;   // [256] group-progress counters of the persistent recurrent kernels
     int enabled = 1;
     int cluster = 2;           // CTAs per cluster of the GEMM core (2 = B-tile multicast pairs, 1 = no clusters)
+    int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
 };
 
 template <typename B>
@@ -661,6 +737,8 @@ static inline int tc_init(TcContext& c) {
     c.enabled = env ? atoi(env) : 1;
     const char* envc = getenv("FSMG_CLUSTER");
     c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
+    const char* envl = getenv("FSMG_LSTM_CLUSTER");
+    c.lstm_cluster = envl ? atoi(envl) : 1;
     int dev = 0;
     FSMG_CUDA_OK(cudaGetDevice(&dev));
     FSMG_CUDA_OK(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -847,18 +925,9 @@ static inline int tc_projection_post(TcContext& c, int n_part, const int32_t* y,
     if (!logits16) {
         tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
     } else {
-        constexpr int ROWS = 16, THREADS = 512;
-        const int groups = cdiv(ld16, THREADS * 8);
-        if (groups <= 3)
-            tc::softmax_grad_fused_kernel<ROWS, THREADS, 3><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, n_part, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
-        else if (groups <= 8)
-            tc::softmax_grad_fused_kernel<ROWS, THREADS, 8><<<cdiv(mc, ROWS), THREADS, 0, s>>>(logits16, ld16, V1, c.part, n_part, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
-        else {
-            tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
-            tc::softmax_grad_inplace_kernel<<<mc, 256, 0, s>>>(logits16, ld16, V1, lse, y, row0);
-            dim3 grid(cdiv(V1, 128), cdiv(mc, 64));
-            colsum_f16_kernel<<<grid, 128, 0, s>>>(logits16, ld16, mc, V1, db_alpha, db, 64);
-        }
+        constexpr int ROWS = 32;
+        dim3 grid(cdiv(ld16, 1024), cdiv(mc, ROWS));
+        tc::softmax_grad_strip_kernel<ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, c.part, n_part, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
     }
     FSMG_LAUNCH_OK();
     return 0;

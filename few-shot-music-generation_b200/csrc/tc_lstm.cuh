@@ -41,6 +41,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, i
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // 32 lanes x 8 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -103,7 +110,9 @@ __host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 
 // =====================================================================================================
 // forward
 // =====================================================================================================
-template <int U, int MT>
+// CLS > 1: the CLS CTAs of a thread-block cluster serve the same group; each fetches every CLS-th K chunk of the
+// exchanged operand and TMA-multicasts it to all of them (L2 -> SMEM traffic / CLS).
+template <int U, int MT, int CLS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, LstmParams p) {
     constexpr int NCOL = 4 * U;                 // accumulator columns per row tile (UMMA N)
@@ -130,13 +139,15 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     const int row_base = p.row_offset + g * p.rows_per_group;                       // first sequence of the group
     const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);     // sequences present (>= 1)
     int* counter = p.counters + g;
+    const int crank = (CLS > 1) ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CLS) - 1u);
     constexpr int BUF_COLS = MT * NCOL;               // one accumulator buffer; two buffers alternate per step
     constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BUF_COLS);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_h);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CLS); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
         mbar_init(&pre_ready[0], 4);
@@ -146,6 +157,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CLS > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -165,7 +177,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], box_bytes);
-                    tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
+                    if (CLS == 1) tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
+                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * lstm_stage_bytes(MT), &map_h, kc * 64, row_base, t - 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -198,7 +211,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                             umma_f16(d_buf + mt * NCOL, a_desc, b_desc, idesc, 1u);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (CLS > 1) umma_commit_mc(&empty_bar[stage], CMASK); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full);
@@ -322,6 +335,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     }
     tc_fence_before();
     __syncthreads();
+    if (CLS > 1) cluster_sync_all();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -331,7 +345,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 //   dh = dh_out[t] + dh_rec ; do = dh*tanh(c) ; dc = dh*o*(1-tanh(c)^2) + dc_next
 //   dgi = dc*j*i(1-i) ; dgj = dc*i*(1-j^2) ; dgf = dc*c_prev*f(1-f) ; dgo = do*o(1-o) ; dc_next' = dc*f
 // =====================================================================================================
-template <int U, int MT>
+template <int U, int MT, int CLS>
 __global__ void __launch_bounds__(LSTM_THREADS, 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dg, LstmParams p) {
     constexpr int NCOL = U;
@@ -355,12 +369,14 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     const int row_base = p.row_offset + g * p.rows_per_group;
     const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);
     int* counter = p.counters + g;
+    const int crank = (CLS > 1) ? (int)cluster_ctarank() : 0;
+    constexpr uint16_t CMASK = (uint16_t)((1u << CLS) - 1u);
     constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
         tma_prefetch_desc(&map_dg);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CLS); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
         fence_barrier_init();
@@ -368,6 +384,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
+    if (CLS > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -384,7 +401,8 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], box_bytes);
-                    tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
+                    if (CLS == 1) tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
+                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * lstm_stage_bytes(MT), &map_dg, kc * 64, row_base, t + 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -410,7 +428,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                             umma_f16(tmem_base + mt * NCOL, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
+                    if (CLS > 1) umma_commit_mc(&empty_bar[stage], CMASK); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full);
@@ -513,6 +531,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     }
     tc_fence_before();
     __syncthreads();
+    if (CLS > 1) cluster_sync_all();
     if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -522,11 +541,11 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 // host side
 // =====================================================================================================
 struct LstmPlan {
-    int U, MT, C, G, rows_per_group, box_rows, rows_per_launch;
+    int U, MT, C, G, rows_per_group, box_rows, rows_per_launch, cls;
     bool ok;
 };
 
-static inline LstmPlan lstm_plan(const TcContext& c, int N, int H) {
+static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, int cls_req = -1) {
     LstmPlan pl;
     memset(&pl, 0, sizeof pl);
     pl.ok = false;
@@ -537,7 +556,13 @@ static inline LstmPlan lstm_plan(const TcContext& c, int N, int H) {
     if (!U) return pl;
     pl.U = U;
     pl.C = H / U;
-    int gmax = c.num_sms / pl.C;
+    int cls = cls_req >= 0 ? cls_req : c.lstm_cluster;
+    if (cls != 1 && cls != 2 && cls != 4) cls = 1;
+    while (cls > 1 && (pl.C % cls) != 0) cls >>= 1;
+    pl.cls = cls;
+    // clusters of 4 cannot use every SM (GPC sizes are not multiples of 4): 132 co-resident CTAs at most
+    const int sms = cls == 4 ? (c.num_sms < 132 ? c.num_sms / 4 * 4 : 132) : c.num_sms;
+    int gmax = sms / pl.C;
     if (gmax < 1) return pl;
     int mg = cdiv(N, gmax);
     if (mg > 256) mg = 256;                       // larger batches are processed in slices of gmax*256 sequences
@@ -565,7 +590,7 @@ static inline int make_map_f16_3d(const TcContext& c, CUtensorMap* map, const vo
 }
 
 template <typename K>
-static inline int lstm_launch(K kernel, int grid, int smem_bytes, const CUtensorMap& mw, const CUtensorMap& mx, const tc::LstmParams& p,
+static inline int lstm_launch(K kernel, int grid, int cls, int smem_bytes, const CUtensorMap& mw, const CUtensorMap& mx, const tc::LstmParams& p,
                               cudaStream_t s) {
     FSMG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg;
@@ -574,14 +599,37 @@ static inline int lstm_launch(K kernel, int grid, int smem_bytes, const CUtensor
     cfg.blockDim = dim3(tc::LSTM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they wait on each other's counters
     attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = cls; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = cls > 1 ? 2 : 1;
     FSMG_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, mw, mx, p));
     return 0;
 }
+
+#define FSMG_LSTM_DISPATCH(KERNEL, RC)                                                                            \
+    do {                                                                                                          \
+        if (pl.U == 32 && pl.MT == 2) {                                                                           \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 2, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 2, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<32, 2, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+        } else if (pl.U == 32) {                                                                                  \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 1, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 1, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<32, 1, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+        } else if (pl.MT == 2) {                                                                                  \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 2, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 2, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<16, 2, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+        } else {                                                                                                  \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 1, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 1, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<16, 1, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+        }                                                                                                         \
+    } while (0)
 
 static inline bool tc_recurrent_supported(TcContext& c, int N, int H) {
     if (!c.ready || !c.enabled || !c.counters) return false;
@@ -611,10 +659,8 @@ static inline int tc_lstm_forward(TcContext& c, const float* pre, const __half* 
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (H / 64) * 4 * pl.U * 128;
         const int smem = tc::lstm_smem_total(w_bytes, pl.MT);
-        if (pl.U == 32 && pl.MT == 2) rc = lstm_launch(tc::lstm_fwd_persistent_kernel<32, 2>, G * pl.C, smem, mw, mh, p, s);
-        else if (pl.U == 32) rc = lstm_launch(tc::lstm_fwd_persistent_kernel<32, 1>, G * pl.C, smem, mw, mh, p, s);
-        else if (pl.MT == 2) rc = lstm_launch(tc::lstm_fwd_persistent_kernel<16, 2>, G * pl.C, smem, mw, mh, p, s);
-        else rc = lstm_launch(tc::lstm_fwd_persistent_kernel<16, 1>, G * pl.C, smem, mw, mh, p, s);
+        const CUtensorMap& mx = mh;
+        FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc);
         if (rc) return rc;
     }
     return 0;
@@ -641,10 +687,8 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (4 * H / 64) * pl.U * 128;
         const int smem = tc::lstm_smem_total(w_bytes, pl.MT);
-        if (pl.U == 32 && pl.MT == 2) rc = lstm_launch(tc::lstm_bwd_persistent_kernel<32, 2>, G * pl.C, smem, mw, md, p, s);
-        else if (pl.U == 32) rc = lstm_launch(tc::lstm_bwd_persistent_kernel<32, 1>, G * pl.C, smem, mw, md, p, s);
-        else if (pl.MT == 2) rc = lstm_launch(tc::lstm_bwd_persistent_kernel<16, 2>, G * pl.C, smem, mw, md, p, s);
-        else rc = lstm_launch(tc::lstm_bwd_persistent_kernel<16, 1>, G * pl.C, smem, mw, md, p, s);
+        const CUtensorMap& mx = md;
+        FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc);
         if (rc) return rc;
     }
     return 0;
