@@ -87,6 +87,12 @@ struct fsmg_handle {
     float *lse = nullptr, *nll = nullptr, *scalars = nullptr, *dws_acc = nullptr;
     float *s_x = nullptr, *s_g = nullptr, *s_logits = nullptr;
     std::vector<float*> s_c, s_h;
+    // sampler v2 (split-fp16 tensor-core contractions, fp32-grade)
+    __half *emb3 = nullptr, *WsT3 = nullptr;
+    std::vector<__half*> KxT3, KhT3, h3;
+    float *P0 = nullptr, *s_logits2 = nullptr;
+    int* s_step = nullptr;
+    bool samp_stale = true;
     int chunk_rows = 0;
     // projection backward overlap: dH / dWs GEMMs of chunk i run on two auxiliary streams while the logits GEMM of
     // chunk i+1 runs on the caller's stream (double-buffered dlogits); fills the tail waves of the persistent GEMMs
@@ -187,6 +193,17 @@ static void carve(fsmg_handle* h, char* base) {
         h->s_c[l] = b.take<float>((int64_t)h->samp_max * h->H);
         h->s_h[l] = b.take<float>((int64_t)h->samp_max * h->H);
     }
+    h->emb3 = b.take<__half>((int64_t)h->V1 * 3 * h->Ep);
+    h->WsT3 = b.take<__half>((int64_t)h->V1 * 3 * h->Hp);
+    h->P0 = b.take<float>((int64_t)h->V1 * h->G4);
+    h->s_logits2 = b.take<float>((int64_t)h->samp_max * h->Vp);
+    h->s_step = b.take<int>(64);
+    h->KxT3.resize(h->L); h->KhT3.resize(h->L); h->h3.resize(h->L);
+    for (int l = 0; l < h->L; ++l) {
+        h->KxT3[l] = b.take<__half>((int64_t)h->G4 * 3 * h->layers[l].inp);
+        h->KhT3[l] = b.take<__half>((int64_t)h->G4 * 3 * h->Hp);
+        h->h3[l] = b.take<__half>((int64_t)h->samp_max * 3 * h->Hp);
+    }
     tc_carve(h->tc, b, h->Nmax, h->T, h->V1, h->Vp, h->H, h->chunk_rows);
     h->ws_need = round_up(b.off, 256);
 }
@@ -215,6 +232,7 @@ static GemmArgs mk(int M, int N, int K, const void* A, int64_t lda, const void* 
 
 static int refresh_weights(fsmg_handle* h, cudaStream_t s) {
     const int TB = 256;
+    h->samp_stale = true;   // the sampler's split-fp16 operand copies are rebuilt lazily
     auto conv = [&](const float* in, int64_t ldi, __half* out, int64_t ldo, int rows, int cols) {
         int64_t total = (int64_t)rows * ldo;
         convert_f16_kernel<<<cdiv(total, TB), TB, 0, s>>>(in, ldi, out, ldo, rows, cols);
@@ -360,7 +378,8 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
         // dWs += loss_scale * hs_chunk^T * dlogits   (contraction over the chunk's tokens)
         {
             ProfScope ps_dws(h, PH_DWS, s_dws);
-            rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 1, 0), true, true, s_dws);
+            // accumulated across chunks with fire-and-forget vector reductions into the L2-resident buffer (no read latency in the epilogue)
+            rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 0, 1), true, true, s_dws);
         }
         if (rc) return rc;
         if (overlap) {
@@ -448,6 +467,69 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
             LAUNCH_COUNT(h);
         }
         cur ^= 1;
+    }
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+// ---- greedy sampler v2: every contraction on the tensor cores with split-fp16 operands (fp32-grade logits) ----
+static int sampler_prepare(fsmg_handle* h, cudaStream_t s) {
+    const int TB = 256, H = h->H;
+    auto wsplit = [&](const float* in, int64_t ldi, __half* out, int Kp, int K, int N) {
+        dim3 grid(cdiv(N, 32), cdiv(Kp, 32));
+        split_weight_t_kernel<<<grid, dim3(32, 8), 0, s>>>(in, ldi, out, Kp, K, N);
+        LAUNCH_COUNT(h);
+    };
+    split_act_kernel<<<cdiv((int64_t)h->V1 * h->Ep, TB), TB, 0, s>>>(h->params + h->emb_off, h->E, h->emb3, h->Ep, h->V1, h->E);
+    LAUNCH_COUNT(h);
+    for (int l = 0; l < h->L; ++l) {
+        LayerBuf& lb = h->layers[l];
+        const float* K = h->params + lb.k_off;
+        wsplit(K, h->G4, h->KxT3[l], lb.inp, lb.in, h->G4);
+        wsplit(K + (int64_t)lb.in * h->G4, h->G4, h->KhT3[l], h->Hp, H, h->G4);
+    }
+    wsplit(h->params + h->sw_off, h->V1, h->WsT3, h->Hp, H, h->V1);
+    FSMG_LAUNCH_OK();
+    // P0[v,:] = embedding[v,:] * Wx_0 + b_0 : the input contraction of layer 0 for every possible word, once
+    int rc = gemm_f16(h, mk(h->V1, h->G4, 3 * h->Ep, h->emb3, 3 * h->Ep, h->KxT3[0], 3 * h->Ep, h->P0, h->G4, 1.0f / 2048.0f,
+                            h->params + h->layers[0].b_off), false, false, s);
+    if (rc) return rc;
+    h->samp_stale = false;
+    return FSMG_OK;
+}
+
+static int sample_greedy_split(fsmg_handle* h, int n, int n_tokens, int32_t* d_out, cudaStream_t s) {
+    const int TB = 256, H = h->H;
+    int rc;
+    if (h->samp_stale && (rc = sampler_prepare(h, s))) return rc;
+    fill_i32_kernel<<<cdiv(n, TB), TB, 0, s>>>(h->samp_ids, n, h->V);   // word = start word (lstm_baseline.py:138)
+    LAUNCH_COUNT(h);
+    FSMG_CUDA_OK(cudaMemsetAsync(h->s_step, 0, sizeof(int), s));
+    for (int l = 0; l < h->L; ++l) {   // zero_state (lstm_baseline.py:140)
+        FSMG_CUDA_OK(cudaMemsetAsync(h->s_c[l], 0, sizeof(float) * n * H, s));
+        FSMG_CUDA_OK(cudaMemsetAsync(h->h3[l], 0, sizeof(__half) * (size_t)n * 3 * h->Hp, s));
+    }
+    const float a = 1.0f / 2048.0f;
+    for (int step = 0; step < n_tokens; ++step) {
+        for (int l = 0; l < h->L; ++l) {
+            // recurrent contraction h_{t-1} * Wh (+ input contraction of the layer below for l > 0)
+            rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l], 3 * h->Hp, h->KhT3[l], 3 * h->Hp, h->s_g, h->G4, a), false, false, s);
+            if (rc) return rc;
+            if (l > 0) {
+                rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l - 1], 3 * h->Hp, h->KxT3[l], 3 * h->Hp, h->s_g, h->G4, a, nullptr, 0, 0, 1), false, false, s);
+                if (rc) return rc;
+            }
+            sample_cell_kernel<<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, l == 0 ? h->P0 : nullptr, h->G4, h->samp_ids,
+                                                                     l == 0 ? nullptr : h->params + h->layers[l].b_off, h->s_c[l], h->h3[l],
+                                                                     h->Hp, n, H);
+            LAUNCH_COUNT(h);
+        }
+        rc = gemm_f16(h, mk(n, h->V1, 3 * h->Hp, h->h3[h->L - 1], 3 * h->Hp, h->WsT3, 3 * h->Hp, h->s_logits2, h->Vp, a,
+                            h->params + h->sb_off), false, false, s);
+        if (rc) return rc;
+        argmax_rows_step_kernel<<<n, 256, 0, s>>>(h->s_logits2, h->Vp, h->V1, h->samp_ids, d_out, n_tokens, h->s_step);
+        bump_counter_kernel<<<1, 32, 0, s>>>(h->s_step);
+        h->launches += 2;
     }
     FSMG_LAUNCH_OK();
     return FSMG_OK;
@@ -653,11 +735,7 @@ int fsmg_sample_greedy(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_
     cudaStream_t s = (cudaStream_t)stream;
     h->launches = 0;
     const int H = h->H, TB = 256, n = n_songs;
-    if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && tc_sampler_supported(h->tc, n, H)) {
-        int rc = tc_sample_greedy(h->tc, n, n_tokens, d_out, s);
-        LAUNCH_COUNT(h);
-        return rc;
-    }
+    if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT)) return sample_greedy_split(h, n, n_tokens, d_out, s);
     fill_i32_kernel<<<cdiv(n, TB), TB, 0, s>>>(h->samp_ids, n, h->V);  // word = start word (lstm_baseline.py:138)
     LAUNCH_COUNT(h);
     for (int l = 0; l < h->L; ++l) {  // zero_state (lstm_baseline.py:140)

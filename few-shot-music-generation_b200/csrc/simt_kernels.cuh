@@ -403,6 +403,120 @@ __global__ void unpad_rows_kernel(const float* __restrict__ src, int64_t lds, fl
     dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
 }
 
+// ============================================================================================
+// Split-fp16 operands for fp32-grade tensor-core contractions (greedy sampler):
+//   x = hi + 2^-11 * lo ,  hi = fp16(x) ,  lo = fp16((x - hi) * 2^11)      (about 22 mantissa bits)
+//   a.b ~= 2^-11 * ( (2^11 a_hi).b_hi + a_hi.b_lo + a_lo.b_hi )            (ONE fp32-accumulating GEMM over 3K)
+// Activations are stored [rows, 3*Kp] = [2^11*hi | hi | lo], weights [N, 3*Kp] = [hi | lo | hi]; the GEMM epilogue
+// applies alpha = 2^-11.  2^11*hi is exact in fp16 for |x| < 32 (activations live in (-1,1), embeddings are small).
+// ============================================================================================
+__device__ __forceinline__ void split_hi_lo(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+}
+// activations: in [rows, cols] fp32 (ldi) -> out [rows, 3*Kp], pads zero
+__global__ void split_act_kernel(const float* __restrict__ in, int64_t ldi, __half* __restrict__ out, int Kp, int rows, int cols) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)rows * Kp) return;
+    int r = (int)(i / Kp), c = (int)(i % Kp);
+    __half hi = __float2half_rn(0.0f), lo = hi;
+    if (c < cols) split_hi_lo(in[(int64_t)r * ldi + c], hi, lo);
+    __half* o = out + (int64_t)r * 3 * Kp;
+    o[c] = __float2half_rn(__half2float(hi) * 2048.0f);
+    o[Kp + c] = hi;
+    o[2 * Kp + c] = lo;
+}
+// weights given as [K rows, N cols] fp32 (TF layout, ldi) -> out [N, 3*Kp] = [hi | lo | hi] of in[k, n]
+__global__ void split_weight_t_kernel(const float* __restrict__ in, int64_t ldi, __half* __restrict__ out, int Kp, int K, int N) {
+    __shared__ float tile[32][33];
+    int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int kk = k0 + j, nn = n0 + threadIdx.x;
+        tile[j][threadIdx.x] = (kk < K && nn < N) ? in[(int64_t)kk * ldi + nn] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        int nn = n0 + j, kk = k0 + threadIdx.x;
+        if (nn < N && kk < Kp) {
+            __half hi = __float2half_rn(0.0f), lo = hi;
+            if (kk < K) split_hi_lo(tile[threadIdx.x][j], hi, lo);
+            __half* o = out + (int64_t)nn * 3 * Kp;
+            o[kk] = hi;
+            o[Kp + kk] = lo;
+            o[2 * Kp + kk] = hi;
+        }
+    }
+}
+
+// Sampler cell step: gates = G[n,:] (+ P[word[n],:] when P != null: the embedding row already multiplied by Wx, bias
+// included) -> c (in place, fp32) -> h -> split [hi | lo] for the next contractions.
+__global__ void sample_cell_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ P, int64_t ldp,
+                                   const int32_t* __restrict__ words, const float* __restrict__ bias,
+                                   float* __restrict__ c_state, __half* __restrict__ h_split, int Hp, int n, int H) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)n * H) return;
+    int r = (int)(idx / H), u = (int)(idx % H);
+    const float* g = G + (int64_t)r * ldg;
+    float gi = g[u], gj = g[H + u], gf = g[2 * H + u], go = g[3 * H + u];
+    if (P) {
+        const float* p = P + (int64_t)words[r] * ldp;
+        gi += p[u]; gj += p[H + u]; gf += p[2 * H + u]; go += p[3 * H + u];
+    } else if (bias) {
+        gi += bias[u]; gj += bias[H + u]; gf += bias[2 * H + u]; go += bias[3 * H + u];
+    }
+    const float i_ = sigmoidf_(gi), j_ = tanhf_(gj), f_ = sigmoidf_(gf + 1.0f), o_ = sigmoidf_(go);
+    const float c = c_state[(int64_t)r * H + u] * f_ + i_ * j_;
+    c_state[(int64_t)r * H + u] = c;
+    const float h = tanhf_(c) * o_;
+    __half hi, lo;
+    split_hi_lo(h, hi, lo);
+    __half* o = h_split + (int64_t)r * 3 * Hp;
+    o[u] = __float2half_rn(__half2float(hi) * 2048.0f);
+    o[Hp + u] = hi;
+    o[2 * Hp + u] = lo;
+}
+
+// argmax with a device-resident step counter (so a captured graph of one decode step can be replayed)
+__global__ void argmax_rows_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, int32_t* __restrict__ next_ids,
+                                        int32_t* __restrict__ out, int64_t out_stride, int* __restrict__ step_counter) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    int r = blockIdx.x;
+    const float* row = logits + (int64_t)r * ld;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+        float v = row[c];
+        if (v > best || (v == best && c < bi)) { best = v; bi = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sv[w] = best; si[w] = bi; }
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        best = lane < nw ? sv[lane] : -INFINITY;
+        bi = lane < nw ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            const int step = *step_counter;
+            next_ids[r] = bi;
+            out[(int64_t)r * out_stride + step] = bi;
+        }
+    }
+}
+__global__ void bump_counter_kernel(int* c) { if (threadIdx.x == 0 && blockIdx.x == 0) *c += 1; }
+
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -321,12 +321,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             int tgt_col = -1;
             if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - n_blk * BN;
             // bias of every chunk of this tile, fetched before the accumulator is awaited (off the critical path)
-            float bias_lane[CHUNKS];
+            // EPI_LSE: the bias of this warp's columns goes to smem once per tile (read back as broadcast float4s)
+            float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(st4) + 2048);
+            if (EPI == EPI_LSE) {
 #pragma unroll
-            for (int cc = 0; cc < CHUNKS; ++cc) {
-                const int colb = n_blk * BN + (half * CHUNKS + cc) * 32 + ((EPI == EPI_LSE) ? lane : 4 * (lane & 7));
-                bias_lane[cc] = 0.0f;
-                if (EPI == EPI_LSE) { if (colb < sh.N) bias_lane[cc] = ep.bias[colb]; }
+                for (int cc = 0; cc < CHUNKS; ++cc) {
+                    const int colb = n_blk * BN + (half * CHUNKS + cc) * 32 + lane;
+                    bias_s[cc * 32 + lane] = colb < sh.N ? ep.bias[colb] : 0.0f;
+                }
+                __syncwarp();
             }
             float4 bias4[CHUNKS];
             if (EPI == EPI_STORE) {
@@ -432,14 +435,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     __syncwarp();   // staging buffer is reused by the next chunk
                 } else {  // EPI_LSE
                     // bias for this chunk: one coalesced load, then broadcast by shuffle
-                    const float bl = bias_lane[cc];
                     float v[32];
                     float cmax = -INFINITY;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float bj = __shfl_sync(0xffffffffu, bl, j);
-                        v[j] = (col0 + j < sh.N) ? __uint_as_float(r[j]) + bj : -INFINITY;
-                        cmax = fmaxf(cmax, v[j]);
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
+                        v[j] = (col0 + j < sh.N) ? __uint_as_float(r[j]) + b4.x : -INFINITY;
+                        v[j + 1] = (col0 + j + 1 < sh.N) ? __uint_as_float(r[j + 1]) + b4.y : -INFINITY;
+                        v[j + 2] = (col0 + j + 2 < sh.N) ? __uint_as_float(r[j + 2]) + b4.z : -INFINITY;
+                        v[j + 3] = (col0 + j + 3 < sh.N) ? __uint_as_float(r[j + 3]) + b4.w : -INFINITY;
+                        cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
                     }
                     const int tj = tgt_col - c * 32;
                     if (row_ok && tj >= 0 && tj < 32) {

@@ -89,11 +89,12 @@ struct LstmParams {
     int* counters;         // [G] monotonic counters (zeroed by the host before the launch)
     int N, T, H, Hp, G4p;
     int ctas_per_group, rows_per_group, box_rows;   // C, M_g, TMA box rows (= M_g rounded to 8)
+    int stage_bytes, stages;   // TMA ring geometry (host-computed: stages sized to the rows actually exchanged)
     int row_offset;        // first sequence handled by this launch (batch slicing when N is large)
     int n_rows;            // sequences handled by this launch
 };
 
-constexpr int LSTM_THREADS = 64 + 128;   // producer warp, MMA warp, 4 epilogue warps
+__host__ __device__ constexpr int lstm_threads(int mt) { return 64 + 128 * mt; }   // producer warp, MMA warp, 4 epilogue warps per row tile
 constexpr int LSTM_MAX_DYN = 227 * 1024;
 
 // smem: [resident weights: KCW chunks x CHUNK_W bytes] [ring: STAGES x (MT*128 rows x 128 B)] [barriers]
@@ -113,18 +114,19 @@ __host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 
 // CLS > 1: the CLS CTAs of a thread-block cluster serve the same group; each fetches every CLS-th K chunk of the
 // exchanged operand and TMA-multicasts it to all of them (L2 -> SMEM traffic / CLS).
 template <int U, int MT, int CLS>
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
+__global__ void __launch_bounds__(lstm_threads(MT), 1)
 lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, LstmParams p) {
     constexpr int NCOL = 4 * U;                 // accumulator columns per row tile (UMMA N)
     constexpr int CHUNK_W = NCOL * 128;         // bytes of the weight slice per 64-wide K chunk
     const int KC = p.H / 64;
     const int W_BYTES = KC * CHUNK_W;
-    const int STAGES = lstm_num_stages(W_BYTES, MT);
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = p.stage_bytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;
     uint8_t* sA = sW + W_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * lstm_stage_bytes(MT));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LSTM_MAX_DYN - 1024 - 256);   // fixed slot at the end of the carve-out
     uint64_t* full_bar = bars;                  // [8]
     uint64_t* empty_bar = bars + 8;             // [8]
     uint64_t* w_bar = bars + 16;
@@ -150,8 +152,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CLS); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
-        mbar_init(&pre_ready[0], 4);
-        mbar_init(&pre_ready[1], 4);
+        mbar_init(&pre_ready[0], 4 * MT);
+        mbar_init(&pre_ready[1], 4 * MT);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -177,8 +179,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], box_bytes);
-                    if (CLS == 1) tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
-                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * lstm_stage_bytes(MT), &map_h, kc * 64, row_base, t - 1, &full_bar[stage], CMASK);
+                    if (CLS == 1) tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
+                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_h, kc * 64, row_base, t - 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -200,7 +202,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(sA + stage * lstm_stage_bytes(MT));
+                    const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
@@ -220,16 +222,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     } else {
         // ===== epilogue: thread <-> (row tile mt, TMEM lane); the cell state c stays in registers for all T steps
         const int quad = warp & 3;
-        float c_state[MT][U];
+        const int mt = (warp - 2) >> 2;          // row tile owned by this warp quartet
+        float c_state[U];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int u = 0; u < U; ++u) c_state[mt][u] = 0.0f;
+        for (int u = 0; u < U; ++u) c_state[u] = 0.0f;
         uint32_t tf_phase = 0;
         // stage pre[t] of this thread's rows into TMEM buffer (t & 1): 4 gates x U columns per row tile
         auto stage_pre = [&](int t) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+            {
                 const int lrow = mt * 128 + quad * 32 + lane;
                 const bool ok = lrow < rows;
                 const float* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * (4 * p.H) + j * U;
@@ -266,8 +266,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pre_ready[(t + 1) & 1]);
                 if (t + 2 < p.T) {   // and pull step t+2's lines towards L2
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
+                    {
                         const int lrow = mt * 128 + quad * 32 + lane;
                         if (lrow < rows) {
                             const float* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * (4 * p.H) + j * U;
@@ -282,8 +281,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 tf_phase ^= 1;
                 tc_fence_after();
             }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+            {
                 const int lrow = mt * 128 + quad * 32 + lane;         // row inside the group
                 const bool ok = lrow < rows;
                 const int64_t r = (int64_t)t * p.N + row_base + lrow; // time-major token row
@@ -310,8 +308,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                             const float j_ = tanh_fast(acc[1][e]);
                             const float f_ = sigmoid_fast(acc[2][e] + 1.0f);   // forget_bias = 1 (A.2)
                             const float o_ = sigmoid_fast(acc[3][e]);
-                            const float cv = c_state[mt][u0 + e] * f_ + i_ * j_;
-                            c_state[mt][u0 + e] = cv;
+                            const float cv = c_state[u0 + e] * f_ + i_ * j_;
+                            c_state[u0 + e] = cv;
                             cn[e] = cv;
                             hq[0][e] = __float2half_rn(i_); hq[1][e] = __float2half_rn(j_);
                             hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
@@ -329,7 +327,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
             // publish: CTA barrier, then ONE gpu-scope release (cumulative over the CTA's stores)
             tc_fence_before();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 128 * MT);
             if (warp == 2 && lane == 0) { __threadfence(); red_release_add(counter, 1); }
         }
     }
@@ -346,18 +344,19 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 //   dgi = dc*j*i(1-i) ; dgj = dc*i*(1-j^2) ; dgf = dc*c_prev*f(1-f) ; dgo = do*o(1-o) ; dc_next' = dc*f
 // =====================================================================================================
 template <int U, int MT, int CLS>
-__global__ void __launch_bounds__(LSTM_THREADS, 1)
+__global__ void __launch_bounds__(lstm_threads(MT), 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dg, LstmParams p) {
     constexpr int NCOL = U;
     constexpr int CHUNK_W = U * 128;
     const int KC = (4 * p.H) / 64;
     const int W_BYTES = KC * CHUNK_W;
-    const int STAGES = lstm_num_stages(W_BYTES, MT);
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = p.stage_bytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sW = smem;
     uint8_t* sA = sW + W_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + STAGES * lstm_stage_bytes(MT));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LSTM_MAX_DYN - 1024 - 256);   // fixed slot at the end of the carve-out
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + 8;
     uint64_t* w_bar = bars + 16;
@@ -401,8 +400,8 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], box_bytes);
-                    if (CLS == 1) tma_load_3d(sA + stage * lstm_stage_bytes(MT), &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
-                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * lstm_stage_bytes(MT), &map_dg, kc * 64, row_base, t + 1, &full_bar[stage], CMASK);
+                    if (CLS == 1) tma_load_3d(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
+                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -417,7 +416,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(sA + stage * lstm_stage_bytes(MT));
+                    const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
@@ -436,17 +435,15 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         }
     } else {
         const int quad = warp & 3;
-        float dc_state[MT][U];
+        const int mt = (warp - 2) >> 2;
+        float dc_state[U];
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt)
-#pragma unroll
-            for (int u = 0; u < U; ++u) dc_state[mt][u] = 0.0f;
+        for (int u = 0; u < U; ++u) dc_state[u] = 0.0f;
         uint32_t tf_phase = 0;
         for (int s = 0; s < p.T; ++s) {
             const int t = p.T - 1 - s;
             if (t > 0) {   // pull the next processed step's stash / upstream-gradient lines towards L2
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
+                {
                     const int lrow = mt * 128 + quad * 32 + lane;
                     if (lrow < rows) {
                         const int64_t rn = (int64_t)(t - 1) * p.N + row_base + lrow;
@@ -462,8 +459,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 tf_phase ^= 1;
                 tc_fence_after();
             }
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
+            {
                 const int lrow = mt * 128 + quad * 32 + lane;
                 const bool ok = lrow < rows;
                 const int64_t r = (int64_t)t * p.N + row_base + lrow;
@@ -512,12 +508,12 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                             const float dhv = dh[e] + acc[e];
                             const float tcv = tanh_fast(cv[e]);
                             const float d_o = dhv * tcv;
-                            const float dc = dhv * o_ * (1.0f - tcv * tcv) + dc_state[mt][u0 + e];
+                            const float dc = dhv * o_ * (1.0f - tcv * tcv) + dc_state[u0 + e];
                             dq[0][e] = __float2half_rn(dc * j_ * i_ * (1.0f - i_));
                             dq[1][e] = __float2half_rn(dc * i_ * (1.0f - j_ * j_));
                             dq[2][e] = __float2half_rn(dc * cp[e] * f_ * (1.0f - f_));
                             dq[3][e] = __float2half_rn(d_o * o_ * (1.0f - o_));
-                            dc_state[mt][u0 + e] = dc * f_;
+                            dc_state[u0 + e] = dc * f_;
                         }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dgo + q * p.H + u0) = *reinterpret_cast<uint4*>(dq[q]);
@@ -525,7 +521,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 }
             }
             tc_fence_before();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 128 * MT);
             if (warp == 2 && lane == 0) { __threadfence(); red_release_add(counter, 1); }
         }
     }
@@ -540,6 +536,19 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 // =====================================================================================================
 // host side
 // =====================================================================================================
+// ring geometry: stages hold exactly the exchanged rows (rounded to the 1024-B swizzle atom); the last stage keeps room for
+// the full MT*128-row window the UMMA descriptors address
+static inline void lstm_ring(int w_bytes, int box_rows, int mt, int* stage_bytes, int* stages) {
+    const int avail = tc::LSTM_MAX_DYN - 1024 - 256 - w_bytes;
+    int sb = (int)round_up((int64_t)box_rows * 128, 1024);
+    int window = mt * 128 * 128;
+    int n = (avail - window) / sb + 1;
+    if (n > 8) n = 8;
+    if (n < 2) { sb = window; n = avail / window; }
+    *stage_bytes = sb;
+    *stages = n;
+}
+
 struct LstmPlan {
     int U, MT, C, G, rows_per_group, box_rows, rows_per_launch, cls;
     bool ok;
@@ -590,13 +599,13 @@ static inline int make_map_f16_3d(const TcContext& c, CUtensorMap* map, const vo
 }
 
 template <typename K>
-static inline int lstm_launch(K kernel, int grid, int cls, int smem_bytes, const CUtensorMap& mw, const CUtensorMap& mx, const tc::LstmParams& p,
+static inline int lstm_launch(K kernel, int grid, int threads, int cls, int smem_bytes, const CUtensorMap& mw, const CUtensorMap& mx, const tc::LstmParams& p,
                               cudaStream_t s) {
     FSMG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(tc::LSTM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
@@ -613,21 +622,21 @@ static inline int lstm_launch(K kernel, int grid, int cls, int smem_bytes, const
 #define FSMG_LSTM_DISPATCH(KERNEL, RC)                                                                            \
     do {                                                                                                          \
         if (pl.U == 32 && pl.MT == 2) {                                                                           \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 2, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 2, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<32, 2, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 2, 4>, G * pl.C, tc::lstm_threads(2), 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 2, 2>, G * pl.C, tc::lstm_threads(2), 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<32, 2, 1>, G * pl.C, tc::lstm_threads(2), 1, smem, mw, mx, p, s);                         \
         } else if (pl.U == 32) {                                                                                  \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 1, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 1, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<32, 1, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 1, 4>, G * pl.C, tc::lstm_threads(1), 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 1, 2>, G * pl.C, tc::lstm_threads(1), 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<32, 1, 1>, G * pl.C, tc::lstm_threads(1), 1, smem, mw, mx, p, s);                         \
         } else if (pl.MT == 2) {                                                                                  \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 2, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 2, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<16, 2, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 2, 4>, G * pl.C, tc::lstm_threads(2), 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 2, 2>, G * pl.C, tc::lstm_threads(2), 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<16, 2, 1>, G * pl.C, tc::lstm_threads(2), 1, smem, mw, mx, p, s);                         \
         } else {                                                                                                  \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 1, 4>, G * pl.C, 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 1, 2>, G * pl.C, 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<16, 1, 1>, G * pl.C, 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 1, 4>, G * pl.C, tc::lstm_threads(1), 4, smem, mw, mx, p, s);             \
+            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 1, 2>, G * pl.C, tc::lstm_threads(1), 2, smem, mw, mx, p, s);        \
+            else RC = lstm_launch(tc::KERNEL<16, 1, 1>, G * pl.C, tc::lstm_threads(1), 1, smem, mw, mx, p, s);                         \
         }                                                                                                         \
     } while (0)
 
@@ -658,7 +667,8 @@ static inline int tc_lstm_forward(TcContext& c, const float* pre, const __half* 
         p.N = N; p.T = T; p.H = H; p.Hp = Hp; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (H / 64) * 4 * pl.U * 128;
-        const int smem = tc::lstm_smem_total(w_bytes, pl.MT);
+        const int smem = tc::LSTM_MAX_DYN;
+        lstm_ring(w_bytes, pl.box_rows, pl.MT, &p.stage_bytes, &p.stages);
         const CUtensorMap& mx = mh;
         FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc);
         if (rc) return rc;
@@ -686,7 +696,8 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         p.N = N; p.T = T; p.H = H; p.Hp = 0; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (4 * H / 64) * pl.U * 128;
-        const int smem = tc::lstm_smem_total(w_bytes, pl.MT);
+        const int smem = tc::LSTM_MAX_DYN;
+        lstm_ring(w_bytes, pl.box_rows, pl.MT, &p.stage_bytes, &p.stages);
         const CUtensorMap& mx = md;
         FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc);
         if (rc) return rc;

@@ -122,10 +122,14 @@ def test_capacity_and_argument_errors(torch_cuda):
     eng.close()
 
 
+SAMPLERS = [pytest.param(0, id="split_fp16_tensor_core"), pytest.param(2, id="fp32_simt")]
+
+
+@pytest.mark.parametrize("flags", SAMPLERS)
 @pytest.mark.parametrize("case", ["tiny_l1", "tiny_l2", "odd_dims", "cfg1_cpu_ref"])
-def test_greedy_sampling_token_indices_bit_exact(torch_cuda, case):
+def test_greedy_sampling_token_indices_bit_exact(torch_cuda, case, flags):
     cfg, g = load_golden(case)
-    eng = make_engine(cfg, 8)
+    eng = make_engine(cfg, 8, flags)
     eng.load_params(O.glorot_init(cfg, 1234))
     n = len(g["sample"])
     got = eng.sample_host(3, n)
@@ -140,12 +144,15 @@ def test_greedy_sampling_token_indices_bit_exact(torch_cuda, case):
     assert i > 0
 
 
-def test_sampling_long_sequence_matches_fp32_oracle(torch_cuda):
+@pytest.mark.parametrize("flags", SAMPLERS)
+def test_sampling_long_sequence_matches_fp32_oracle(torch_cuda, flags):
     cfg = dict(name="lstm_baseline", input_size=4708, embedding_size=96, hidden_size=128, n_layers=1, max_len=16)
     params = O.glorot_init(cfg, 77)
-    eng = make_engine(cfg, 4)
+    eng = make_engine(cfg, 4, flags)
     eng.load_params(params)
     got = eng.sample_host(2, 96)[0].tolist()
+    got_again = eng.sample_host(2, 96)[0].tolist()     # second call: cached split operands / P table
+    assert got == got_again
     want, margins = O.sample_greedy(params, 96, np.float64, True)
     for i, (a, b) in enumerate(zip(got, want)):
         if a != b:
@@ -237,3 +244,24 @@ def test_train_entry_point_end_to_end(torch_cuda, tmp_path):
     assert "Iter: 6, val-nll" in out.stdout and "Test Avg NLL" in out.stdout
     assert (tmp_path / "ck" / "lstm_baseline" / "lstm_baseline-6.npz").exists()
     assert (tmp_path / "ck" / "samples" / "sample_0" / "model_sample.txt").exists()
+
+
+def test_sampling_after_training_uses_fresh_weights(torch_cuda):
+    """The sampler's cached operand copies are rebuilt after an optimizer step."""
+    cfg = dict(name="lstm_baseline", input_size=300, embedding_size=32, hidden_size=64, n_layers=2, max_len=8, lr=5e-2,
+               n_decay=10000, max_grad_norm=5)
+    params = O.glorot_init(cfg, 3)
+    eng = make_engine(cfg, 45)
+    eng.load_params(params)
+    before = eng.sample_host(1, 24)[0].tolist()
+    tok = O.synthetic_tokens(np.random.RandomState(1), (45, 8), 300, "zipf")
+    for _ in range(5):
+        eng.train_host(tok)
+    after = eng.sample_host(1, 24)[0].tolist()
+    new_params = {k: v.astype(np.float32) for k, v in eng.export().items()}
+    want, margins = O.sample_greedy(new_params, 24, np.float64, True)
+    for i, (a, b) in enumerate(zip(after, want)):
+        if a != b:
+            assert margins[i] < TIE_MARGIN, (i, a, b, margins[i])
+            break
+    assert before != after or before == want
