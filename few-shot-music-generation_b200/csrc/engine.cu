@@ -81,7 +81,7 @@ struct fsmg_handle {
     int64_t ws_bytes = 0, ws_need = 0;
     bool bound = false;
     // workspace carve-up
-    int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *samp_ids = nullptr, *samp_out = nullptr;
+    int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *samp_ids = nullptr, *samp_out = nullptr, *samp_out2 = nullptr;
     __half *emb16 = nullptr, *Ws16 = nullptr, *WsT16 = nullptr, *xemb = nullptr, *dgates = nullptr, *dlogits = nullptr;
     float *pre = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
     float *lse = nullptr, *nll = nullptr, *scalars = nullptr, *dws_acc = nullptr;
@@ -93,6 +93,8 @@ struct fsmg_handle {
     float *P0 = nullptr, *s_logits2 = nullptr;
     int* s_step = nullptr;
     bool samp_stale = true;
+    cudaGraphExec_t samp_graph = nullptr;   // one captured decode step (replayed n_tokens times)
+    int samp_graph_n = 0;
     int chunk_rows = 0;
     // projection backward overlap: dH / dWs GEMMs of chunk i run on two auxiliary streams while the logits GEMM of
     // chunk i+1 runs on the caller's stream (double-buffered dlogits); fills the tail waves of the persistent GEMMs
@@ -169,7 +171,7 @@ static void carve(fsmg_handle* h, char* base) {
     const char* env_mb = getenv("FSMG_CHUNK_MB");
     const char* env_ov = getenv("FSMG_OVERLAP");
     h->overlap = env_ov ? atoi(env_ov) : 1;
-    const int64_t chunk_mb = env_mb ? atoi(env_mb) : (h->overlap ? 32 : 48);   // two chunks are in flight when overlapping
+    const int64_t chunk_mb = env_mb ? atoi(env_mb) : 256;   // measured optimum (sweep 32..768 MB): launch efficiency beats L2 residency
     int64_t rows = (chunk_mb << 20) / ((int64_t)h->Vp * 2);
     rows = rows / 128 * 128;
     if (rows < 128) rows = 128;
@@ -184,6 +186,7 @@ static void carve(fsmg_handle* h, char* base) {
     h->samp_max = h->Nmax;
     h->samp_ids = b.take<int32_t>(h->samp_max);
     h->samp_out = b.take<int32_t>((int64_t)h->samp_max * 4096);
+    h->samp_out2 = b.take<int32_t>((int64_t)h->samp_max * 4096);
     h->s_x = b.take<float>((int64_t)h->samp_max * wmax);
     h->s_g = b.take<float>((int64_t)h->samp_max * h->G4);
     h->s_logits = b.take<float>((int64_t)h->samp_max * h->V1);
@@ -498,9 +501,37 @@ static int sampler_prepare(fsmg_handle* h, cudaStream_t s) {
     return FSMG_OK;
 }
 
+// one decode step for n songs: recurrent (+ lower-layer) contractions, cell, projection, argmax, step counter
+static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
+    const int TB = 256, H = h->H;
+    const float a = 1.0f / 2048.0f;
+    int rc;
+    for (int l = 0; l < h->L; ++l) {
+        rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l], 3 * h->Hp, h->KhT3[l], 3 * h->Hp, h->s_g, h->G4, a), false, false, s);
+        if (rc) return rc;
+        if (l > 0) {
+            rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l - 1], 3 * h->Hp, h->KxT3[l], 3 * h->Hp, h->s_g, h->G4, a, nullptr, 0, 0, 1), false, false, s);
+            if (rc) return rc;
+        }
+        sample_cell_kernel<<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, l == 0 ? h->P0 : nullptr, h->G4, h->samp_ids,
+                                                                 l == 0 ? nullptr : h->params + h->layers[l].b_off, h->s_c[l], h->h3[l],
+                                                                 h->Hp, n, H);
+        LAUNCH_COUNT(h);
+    }
+    rc = gemm_f16(h, mk(n, h->V1, 3 * h->Hp, h->h3[h->L - 1], 3 * h->Hp, h->WsT3, 3 * h->Hp, h->s_logits2, h->Vp, a,
+                        h->params + h->sb_off), false, false, s);
+    if (rc) return rc;
+    argmax_rows_step_kernel<<<n, 256, 0, s>>>(h->s_logits2, h->Vp, h->V1, h->samp_ids, h->samp_out, 4096, h->s_step);
+    bump_counter_kernel<<<1, 32, 0, s>>>(h->s_step);
+    h->launches += 2;
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
 static int sample_greedy_split(fsmg_handle* h, int n, int n_tokens, int32_t* d_out, cudaStream_t s) {
     const int TB = 256, H = h->H;
     int rc;
+    if (n_tokens > 4096) return set_error(FSMG_ERR_CAPACITY, "n_tokens > 4096");
     if (h->samp_stale && (rc = sampler_prepare(h, s))) return rc;
     fill_i32_kernel<<<cdiv(n, TB), TB, 0, s>>>(h->samp_ids, n, h->V);   // word = start word (lstm_baseline.py:138)
     LAUNCH_COUNT(h);
@@ -509,29 +540,33 @@ static int sample_greedy_split(fsmg_handle* h, int n, int n_tokens, int32_t* d_o
         FSMG_CUDA_OK(cudaMemsetAsync(h->s_c[l], 0, sizeof(float) * n * H, s));
         FSMG_CUDA_OK(cudaMemsetAsync(h->h3[l], 0, sizeof(__half) * (size_t)n * 3 * h->Hp, s));
     }
-    const float a = 1.0f / 2048.0f;
-    for (int step = 0; step < n_tokens; ++step) {
-        for (int l = 0; l < h->L; ++l) {
-            // recurrent contraction h_{t-1} * Wh (+ input contraction of the layer below for l > 0)
-            rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l], 3 * h->Hp, h->KhT3[l], 3 * h->Hp, h->s_g, h->G4, a), false, false, s);
-            if (rc) return rc;
-            if (l > 0) {
-                rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l - 1], 3 * h->Hp, h->KxT3[l], 3 * h->Hp, h->s_g, h->G4, a, nullptr, 0, 0, 1), false, false, s);
-                if (rc) return rc;
-            }
-            sample_cell_kernel<<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, l == 0 ? h->P0 : nullptr, h->G4, h->samp_ids,
-                                                                     l == 0 ? nullptr : h->params + h->layers[l].b_off, h->s_c[l], h->h3[l],
-                                                                     h->Hp, n, H);
-            LAUNCH_COUNT(h);
+    const char* env_g = getenv("FSMG_SAMPLE_GRAPH");
+    const bool use_graph = (env_g ? atoi(env_g) != 0 : true) && h->aux[0] != nullptr && n_tokens >= 4;
+    if (use_graph) {
+        // the decode step is identical for every token (the step index lives on the device): capture it once on an
+        // internal stream and replay the graph — one launch per generated token instead of ~8
+        if (!h->samp_graph || h->samp_graph_n != n) {
+            if (h->samp_graph) { cudaGraphExecDestroy(h->samp_graph); h->samp_graph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            FSMG_CUDA_OK(cudaStreamBeginCapture(h->aux[0], cudaStreamCaptureModeThreadLocal));
+            int64_t saved = h->launches;
+            rc = sample_step_split(h, n, h->aux[0]);
+            h->launches = saved;
+            cudaError_t ce = cudaStreamEndCapture(h->aux[0], &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (ce != cudaSuccess) return set_error(FSMG_ERR_CUDA, "graph capture of the decode step failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&h->samp_graph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return set_error(FSMG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+            h->samp_graph_n = n;
         }
-        rc = gemm_f16(h, mk(n, h->V1, 3 * h->Hp, h->h3[h->L - 1], 3 * h->Hp, h->WsT3, 3 * h->Hp, h->s_logits2, h->Vp, a,
-                            h->params + h->sb_off), false, false, s);
-        if (rc) return rc;
-        argmax_rows_step_kernel<<<n, 256, 0, s>>>(h->s_logits2, h->Vp, h->V1, h->samp_ids, d_out, n_tokens, h->s_step);
-        bump_counter_kernel<<<1, 32, 0, s>>>(h->s_step);
-        h->launches += 2;
+        for (int step = 0; step < n_tokens; ++step) FSMG_CUDA_OK(cudaGraphLaunch(h->samp_graph, s));
+        h->launches += n_tokens;
+    } else {
+        for (int step = 0; step < n_tokens; ++step)
+            if ((rc = sample_step_split(h, n, s))) return rc;
     }
-    FSMG_LAUNCH_OK();
+    FSMG_CUDA_OK(cudaMemcpy2DAsync(d_out, (size_t)n_tokens * 4, h->samp_out, 4096 * 4, (size_t)n_tokens * 4, n, cudaMemcpyDeviceToDevice, s));
     return FSMG_OK;
 }
 
@@ -601,6 +636,7 @@ void fsmg_destroy(fsmg_handle* h) {
     if (h->h_tok) cudaFreeHost(h->h_tok);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (auto ev : h->prof.pool) cudaEventDestroy(ev);
+    if (h->samp_graph) cudaGraphExecDestroy(h->samp_graph);
     for (int i = 0; i < 2; ++i) {
         if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
         if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
@@ -820,9 +856,9 @@ int fsmg_sample_host(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t*
     if (!h || !h->bound) return set_error(FSMG_ERR_STATE, "not bound");
     if (n_tokens > 4096) return set_error(FSMG_ERR_CAPACITY, "n_tokens > 4096");
     cudaStream_t s = (cudaStream_t)stream;
-    int rc = fsmg_sample_greedy(h, n_songs, n_tokens, h->samp_out, s);
+    int rc = fsmg_sample_greedy(h, n_songs, n_tokens, h->samp_out2, s);
     if (rc) return rc;
-    FSMG_CUDA_OK(cudaMemcpyAsync(h_out, h->samp_out, (int64_t)n_songs * n_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    FSMG_CUDA_OK(cudaMemcpyAsync(h_out, h->samp_out2, (int64_t)n_songs * n_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     FSMG_CUDA_OK(cudaStreamSynchronize(s));
     return FSMG_OK;
 }

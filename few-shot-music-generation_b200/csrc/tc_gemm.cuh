@@ -176,9 +176,46 @@ struct EpiParams {
 struct GemmShape {
     int M, N, K;
     int n_m, n_n, n_s;      // tiles along M, N and K-splits
+    int streamk;            // 1: each cluster owns a contiguous range of (cluster-tile, k-block) units (balanced; RED epilogue)
+    int units_per_cluster;  // stream-K: k-block units per cluster
     int n_mp;               // M tiles per cluster-tile row = ceil(n_m / CL): a cluster of CL CTAs owns CL consecutive M tiles of one N tile
     int kb_per_split;       // k-blocks per split
     int kb_total;
+};
+
+// Work iterator shared by the three warp roles.  mode 0: cluster-tiles (optionally K-split) strided over the clusters;
+// mode 1 (stream-K): a contiguous range of k-block units, cut into (tile, kb0, kb1) pieces at tile boundaries.
+struct WorkIter {
+    int cur, end, stride;
+    __device__ __forceinline__ WorkIter(const GemmShape& sh, int cluster_id, int n_clusters) {
+        if (sh.streamk) {
+            const int total = sh.n_mp * sh.n_n * sh.kb_total;
+            cur = min(total, cluster_id * sh.units_per_cluster);
+            end = min(total, cur + sh.units_per_cluster);
+            stride = 0;
+        } else {
+            cur = cluster_id;
+            end = sh.n_mp * sh.n_n * sh.n_s;
+            stride = n_clusters;
+        }
+    }
+    __device__ __forceinline__ bool next(const GemmShape& sh, int& tile_mn, int& kb0, int& kb1) {
+        if (cur >= end) return false;
+        if (sh.streamk) {
+            tile_mn = cur / sh.kb_total;
+            kb0 = cur - tile_mn * sh.kb_total;
+            kb1 = min(sh.kb_total, kb0 + (end - cur));
+            cur += kb1 - kb0;
+        } else {
+            const int tiles_mn = sh.n_mp * sh.n_n;
+            tile_mn = cur % tiles_mn;
+            const int s_blk = cur / tiles_mn;
+            kb0 = s_blk * sh.kb_per_split;
+            kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
+            cur += stride;
+        }
+        return true;
+    }
 };
 
 template <int BN>
@@ -201,7 +238,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     using L = SmemLayout<BN>;
     constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // keep the pointer in the shared address space (pointer arithmetic on the extern array, no integer round trip):
+    // otherwise the staging accesses compile to generic LD/ST instead of LDS/STS
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* epi_smem = smem + STAGES * L::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + L::EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
@@ -210,10 +249,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total_tiles = sh.n_mp * sh.n_n * sh.n_s;          // cluster-tiles
     const int cta_rank = (CL == 2) ? (int)cluster_ctarank() : 0;
-    const int first_tile = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int tile_stride = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int cluster_id = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_clusters = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
@@ -233,10 +271,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-                const int m_blk = (tile % sh.n_mp) * CL + cta_rank, n_blk = (tile / sh.n_mp) % sh.n_n, s_blk = tile / (sh.n_mp * sh.n_n);
-                const int kb0 = s_blk * sh.kb_per_split;
-                const int kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
+            WorkIter it(sh, cluster_id, n_clusters);
+            int tile_mn, kb0, kb1;
+            while (it.next(sh, tile_mn, kb0, kb1)) {
+                const int m_blk = (tile_mn % sh.n_mp) * CL + cta_rank, n_blk = tile_mn / sh.n_mp;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
@@ -276,10 +314,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-                const int s_blk = tile / (sh.n_mp * sh.n_n);
-                const int kb0 = s_blk * sh.kb_per_split;
-                const int kb1 = min(sh.kb_total, kb0 + sh.kb_per_split);
+            WorkIter it(sh, cluster_id, n_clusters);
+            int tile_mn, kb0, kb1;
+            while (it.next(sh, tile_mn, kb0, kb1)) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -311,8 +348,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         constexpr int CHUNKS = BN / 64;                        // 32-column chunks per warp
         float4* st4 = reinterpret_cast<float4*>(epi_smem + (warp - 2) * EPI_STAGE_BYTES);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-            const int m_blk = (tile % sh.n_mp) * CL + cta_rank, n_blk = (tile / sh.n_mp) % sh.n_n, s_blk = tile / (sh.n_mp * sh.n_n);
+        WorkIter it(sh, cluster_id, n_clusters);
+        int tile_mn, kb0, kb1;
+        while (it.next(sh, tile_mn, kb0, kb1)) {
+            const int m_blk = (tile_mn % sh.n_mp) * CL + cta_rank, n_blk = tile_mn / sh.n_mp;
             const int row_w0 = m_blk * BM + quad * 32;            // first row of this warp
             const int row = row_w0 + lane;                         // row held by this thread in TMEM
             const bool row_ok = row < sh.M;
@@ -333,7 +372,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             float4 bias4[CHUNKS];
             if (EPI == EPI_STORE) {
-                const bool add_bias = ep.bias != nullptr && s_blk == 0;
+                const bool add_bias = ep.bias != nullptr && kb0 == 0;   // the piece that starts the K range carries the bias
 #pragma unroll
                 for (int cc = 0; cc < CHUNKS; ++cc) {
                     const int colv = n_blk * BN + (half * CHUNKS + cc) * 32 + 4 * (lane & 7);
@@ -437,14 +476,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // bias for this chunk: one coalesced load, then broadcast by shuffle
                     float v[32];
                     float cmax = -INFINITY;
+                    if (full) {   // warp-uniform fast path: no per-element column guards
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
-                        v[j] = (col0 + j < sh.N) ? __uint_as_float(r[j]) + b4.x : -INFINITY;
-                        v[j + 1] = (col0 + j + 1 < sh.N) ? __uint_as_float(r[j + 1]) + b4.y : -INFINITY;
-                        v[j + 2] = (col0 + j + 2 < sh.N) ? __uint_as_float(r[j + 2]) + b4.z : -INFINITY;
-                        v[j + 3] = (col0 + j + 3 < sh.N) ? __uint_as_float(r[j + 3]) + b4.w : -INFINITY;
-                        cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
+                            v[j] = __uint_as_float(r[j]) + b4.x;
+                            v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
+                            v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
+                            v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
+                            cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
+                            v[j] = (col0 + j < sh.N) ? __uint_as_float(r[j]) + b4.x : -INFINITY;
+                            v[j + 1] = (col0 + j + 1 < sh.N) ? __uint_as_float(r[j + 1]) + b4.y : -INFINITY;
+                            v[j + 2] = (col0 + j + 2 < sh.N) ? __uint_as_float(r[j + 2]) + b4.z : -INFINITY;
+                            v[j + 3] = (col0 + j + 3 < sh.N) ? __uint_as_float(r[j + 3]) + b4.w : -INFINITY;
+                            cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
+                        }
                     }
                     const int tj = tgt_col - c * 32;
                     if (row_ok && tj >= 0 && tj < 32) {
@@ -454,9 +505,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         ep.tgt[row] = tv;
                     }
                     const float nmax = fmaxf(run_max, cmax);
+                    const float nmax_l2 = nmax * 1.4426950408889634f;
                     float sacc = 0.0f;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sacc += __expf(v[j] - nmax);
+                    for (int j = 0; j < 32; ++j) sacc += exp2f(fmaf(v[j], 1.4426950408889634f, -nmax_l2));   // one FFMA + MUFU.EX2
                     run_sum = run_sum * __expf(run_max - nmax) + sacc;
                     run_max = nmax;
                     if (ep.logits16) {
@@ -723,9 +775,11 @@ struct TcContext {
     float* tgt = nullptr;
     int part_tiles = 0;
     int* counters = nullptr;   // [256] group-progress counters of the persistent recurrent kernels
+    long long* trace = nullptr; // [128] debug timeline (FSMG_TRACE=1)
     int enabled = 1;
     int cluster = 2;           // CTAs per cluster of the GEMM core (2 = B-tile multicast pairs, 1 = no clusters)
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
+    int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
 };
 
 template <typename B>
@@ -734,6 +788,7 @@ static inline void tc_carve(TcContext& c, B& b, int /*Nmax*/, int /*T*/, int V1,
     c.part = b.template take<float2>((int64_t)chunk_rows * c.part_tiles);
     c.tgt = b.template take<float>(chunk_rows);
     c.counters = b.template take<int>(256);
+    c.trace = b.template take<long long>(128);
 }
 
 static inline int tc_init(TcContext& c) {
@@ -742,6 +797,8 @@ static inline int tc_init(TcContext& c) {
     c.enabled = env ? atoi(env) : 1;
     const char* envc = getenv("FSMG_CLUSTER");
     c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
+    const char* envs = getenv("FSMG_STREAMK");
+    c.streamk = envs ? atoi(envs) : 1;
     const char* envl = getenv("FSMG_LSTM_CLUSTER");
     c.lstm_cluster = envl ? atoi(envl) : 1;
     int dev = 0;
@@ -825,6 +882,23 @@ static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow
     sh.n_s = cdiv(sh.kb_total, sh.kb_per_split);
     int total = tiles * sh.n_s;
     p.grid = (total < slots ? total : slots) * p.cl;
+    sh.streamk = 0;
+    sh.units_per_cluster = 0;
+    if (allow_split && c.streamk) {
+        // wave quantisation of the plain schedule; below 90 % switch to stream-K (perfectly balanced k-block ranges)
+        const int rounds = cdiv(total, slots);
+        const double eff = (double)total / ((double)rounds * slots);
+        const int64_t units = (int64_t)tiles * sh.kb_total;
+        if (eff < 0.90 && units >= 16) {
+            int ncl = slots;
+            int upc = (int)cdiv(units, ncl);
+            if (upc < 8) { upc = 8; ncl = (int)cdiv(units, upc); }
+            sh.streamk = 1;
+            sh.units_per_cluster = upc;
+            sh.n_s = 2;                       // marks "partial sums are combined with atomics" for the caller
+            p.grid = (int)cdiv(units, upc) * p.cl;
+        }
+    }
     return p;
 }
 

@@ -76,6 +76,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+#define FSMG_TR(step, slot)                                                                      \
+    do {                                                                                         \
+        if (p.trace && blockIdx.x == 0 && (step) >= 8 && (step) < 16) p.trace[((step) - 8) * 16 + (slot)] = clock64(); \
+    } while (0)
+
 struct LstmParams {
     // forward
     const float* pre;      // [T*N, 4H] fp32: x_t * Wx + b (hoisted input contraction)
@@ -89,6 +94,7 @@ struct LstmParams {
     int* counters;         // [G] monotonic counters (zeroed by the host before the launch)
     int N, T, H, Hp, G4p;
     int ctas_per_group, rows_per_group, box_rows;   // C, M_g, TMA box rows (= M_g rounded to 8)
+    long long* trace;          // debug: clock64 timeline of CTA 0 for steps [8, 16) (FSMG_TRACE=1), else null
     int stage_bytes, stages;   // TMA ring geometry (host-computed: stages sized to the rows actually exchanged)
     int row_offset;        // first sequence handled by this launch (batch slicing when N is large)
     int n_rows;            // sequences handled by this launch
@@ -123,7 +129,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     const int STAGES = p.stages;
     const int STAGE_BYTES = p.stage_bytes;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     uint8_t* sW = smem;
     uint8_t* sA = sW + W_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LSTM_MAX_DYN - 1024 - 256);   // fixed slot at the end of the carve-out
@@ -175,6 +181,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             for (int t = 1; t < p.T; ++t) {
                 const int need = p.ctas_per_group * t;      // all C CTAs of the group have published h_{t-1}
                 while (ld_acquire(counter) < need) { }
+                FSMG_TR(t, 0);
                 fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -183,6 +190,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_h, kc * 64, row_base, t - 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                FSMG_TR(t, 1);
             }
         }
     } else if (warp == 1) {
@@ -201,6 +209,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 const uint32_t d_buf = tmem_base + (uint32_t)((t & 1) * BUF_COLS);
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (kc == 0) FSMG_TR(t, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
@@ -217,6 +226,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full);
+                FSMG_TR(t, 3);
             }
         }
     } else {
@@ -265,6 +275,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&pre_ready[(t + 1) & 1]);
+                if (warp == 2 && lane == 0) FSMG_TR(t, 4);
                 if (t + 2 < p.T) {   // and pull step t+2's lines towards L2
                     {
                         const int lrow = mt * 128 + quad * 32 + lane;
@@ -281,6 +292,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 tf_phase ^= 1;
                 tc_fence_after();
             }
+            if (warp == 2 && lane == 0) FSMG_TR(t, 5);
             {
                 const int lrow = mt * 128 + quad * 32 + lane;         // row inside the group
                 const bool ok = lrow < rows;
@@ -327,8 +339,9 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
             // publish: CTA barrier, then ONE gpu-scope release (cumulative over the CTA's stores)
             tc_fence_before();
+            if (warp == 2 && lane == 0) FSMG_TR(t, 6);
             named_bar_sync(1, 128 * MT);
-            if (warp == 2 && lane == 0) { __threadfence(); red_release_add(counter, 1); }
+            if (warp == 2 && lane == 0) { FSMG_TR(t, 7); __threadfence(); red_release_add(counter, 1); FSMG_TR(t, 8); }
         }
     }
     tc_fence_before();
@@ -353,7 +366,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     const int STAGES = p.stages;
     const int STAGE_BYTES = p.stage_bytes;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-space pointer
     uint8_t* sW = smem;
     uint8_t* sA = sW + W_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LSTM_MAX_DYN - 1024 - 256);   // fixed slot at the end of the carve-out
@@ -396,6 +409,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             for (int s = 1; s < p.T; ++s) {             // s-th processed step handles t = T-1-s and needs dgates_{t+1}
                 const int t = p.T - 1 - s;
                 while (ld_acquire(counter) < p.ctas_per_group * s) { }
+                FSMG_TR(s, 0);
                 fence_proxy_async_all();
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -404,6 +418,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                FSMG_TR(s, 1);
             }
         }
     } else if (warp == 1) {
@@ -415,6 +430,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             for (int s = 1; s < p.T; ++s) {
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (kc == 0) FSMG_TR(s, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
@@ -431,6 +447,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tmem_full);
+                FSMG_TR(s, 3);
             }
         }
     } else {
@@ -459,6 +476,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 tf_phase ^= 1;
                 tc_fence_after();
             }
+            if (warp == 2 && lane == 0) FSMG_TR(s, 5);
             {
                 const int lrow = mt * 128 + quad * 32 + lane;
                 const bool ok = lrow < rows;
@@ -521,8 +539,9 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 }
             }
             tc_fence_before();
+            if (warp == 2 && lane == 0) FSMG_TR(s, 6);
             named_bar_sync(1, 128 * MT);
-            if (warp == 2 && lane == 0) { __threadfence(); red_release_add(counter, 1); }
+            if (warp == 2 && lane == 0) { FSMG_TR(s, 7); __threadfence(); red_release_add(counter, 1); FSMG_TR(s, 8); }
         }
     }
     tc_fence_before();
@@ -640,6 +659,20 @@ static inline int lstm_launch(K kernel, int grid, int threads, int cls, int smem
         }                                                                                                         \
     } while (0)
 
+static inline void lstm_trace_dump(TcContext& c, const char* what, cudaStream_t s) {
+    cudaStreamSynchronize(s);
+    long long host[8 * 16];
+    cudaMemcpy(host, c.trace, sizeof host, cudaMemcpyDeviceToHost);
+    static const char* names[9] = {"P:counter_ok", "P:tma_issued", "M:first_full", "M:commit", "E:staged", "E:tmem_full", "E:computed", "E:barrier", "E:published"};
+    fprintf(stderr, "[fsmg trace] %s (CTA 0, clock64 cycles relative to step's E:tmem_full of previous row)\n", what);
+    for (int st = 1; st < 8; ++st) {
+        long long base = host[(st - 1) * 16 + 8];   // previous step's publish
+        fprintf(stderr, "  step %2d:", st + 8);
+        for (int k = 0; k < 9; ++k) fprintf(stderr, " %s=%lld", names[k], host[st * 16 + k] ? host[st * 16 + k] - base : -1);
+        fprintf(stderr, "\n");
+    }
+}
+
 static inline bool tc_recurrent_supported(TcContext& c, int N, int H) {
     if (!c.ready || !c.enabled || !c.counters) return false;
     const char* env = getenv("FSMG_PERSISTENT");
@@ -670,7 +703,10 @@ static inline int tc_lstm_forward(TcContext& c, const float* pre, const __half* 
         const int smem = tc::LSTM_MAX_DYN;
         lstm_ring(w_bytes, pl.box_rows, pl.MT, &p.stage_bytes, &p.stages);
         const CUtensorMap& mx = mh;
+        const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
+        if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
         FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc);
+        if (trace && !rc) lstm_trace_dump(c, "lstm_fwd_persistent", s);
         if (rc) return rc;
     }
     return 0;
@@ -699,7 +735,10 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         const int smem = tc::LSTM_MAX_DYN;
         lstm_ring(w_bytes, pl.box_rows, pl.MT, &p.stage_bytes, &p.stages);
         const CUtensorMap& mx = md;
+        const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
+        if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
         FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc);
+        if (trace && !rc) lstm_trace_dump(c, "lstm_bwd_persistent", s);
         if (rc) return rc;
     }
     return 0;
