@@ -56,6 +56,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns, registers -> TMEM
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -293,11 +296,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 tc_fence_after();
             }
             if (warp == 2 && lane == 0) FSMG_TR(t, 5);
+            const int lrow = mt * 128 + quad * 32 + lane;         // row inside the group
+            const bool ok = lrow < rows;
+            const int64_t r = (int64_t)t * p.N + row_base + lrow; // time-major token row
+            // BPTT stash of this step (gates fp16, c fp32): kept in registers and written AFTER h has been published,
+            // so the release fence only has to drain the 64-byte h stores the rest of the group is waiting for
+            uint4 g_stash[U / 8][4];
+            float4 c_stash[U / 8][2];
             {
-                const int lrow = mt * 128 + quad * 32 + lane;         // row inside the group
-                const bool ok = lrow < rows;
-                const int64_t r = (int64_t)t * p.N + row_base + lrow; // time-major token row
-                __half* gout = p.gates + r * p.G4p + j * U;
                 const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + mt * NCOL + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int u0 = 0; u0 < U; u0 += 8) {
@@ -310,38 +316,45 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                         for (int e = 0; e < 8; ++e) acc[q][e] = __uint_as_float(rr[e]);
                     }
                     tmem_ld_wait();
-                    if (ok) {
-                        __align__(16) __half hq[4][8];
-                        __align__(16) __half hh[8];
-                        float cn[8];
+                    __align__(16) __half hq[4][8];
+                    __align__(16) __half hh[8];
+                    float cn[8];
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const float i_ = sigmoid_fast(acc[0][e]);
-                            const float j_ = tanh_fast(acc[1][e]);
-                            const float f_ = sigmoid_fast(acc[2][e] + 1.0f);   // forget_bias = 1 (A.2)
-                            const float o_ = sigmoid_fast(acc[3][e]);
-                            const float cv = c_state[u0 + e] * f_ + i_ * j_;
-                            c_state[u0 + e] = cv;
-                            cn[e] = cv;
-                            hq[0][e] = __float2half_rn(i_); hq[1][e] = __float2half_rn(j_);
-                            hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
-                            hh[e] = __float2half_rn(tanh_fast(cv) * o_);
-                        }
-                        // h first: it is what the other CTAs of the group are waiting for
-                        *reinterpret_cast<uint4*>(p.hs + r * p.Hp + j * U + u0) = *reinterpret_cast<uint4*>(hh);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(gout + q * p.H + u0) = *reinterpret_cast<uint4*>(hq[q]);
-                        float* cdst = p.c + r * p.H + j * U + u0;
-                        *reinterpret_cast<float4*>(cdst) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                        *reinterpret_cast<float4*>(cdst + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                    for (int e = 0; e < 8; ++e) {
+                        const float i_ = sigmoid_fast(acc[0][e]);
+                        const float j_ = tanh_fast(acc[1][e]);
+                        const float f_ = sigmoid_fast(acc[2][e] + 1.0f);   // forget_bias = 1 (A.2)
+                        const float o_ = sigmoid_fast(acc[3][e]);
+                        const float cv = c_state[u0 + e] * f_ + i_ * j_;
+                        c_state[u0 + e] = cv;
+                        cn[e] = cv;
+                        hq[0][e] = __float2half_rn(i_); hq[1][e] = __float2half_rn(j_);
+                        hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
+                        hh[e] = __float2half_rn(tanh_fast(cv) * o_);
                     }
+                    if (ok) *reinterpret_cast<uint4*>(p.hs + r * p.Hp + j * U + u0) = *reinterpret_cast<uint4*>(hh);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) g_stash[u0 / 8][q] = *reinterpret_cast<uint4*>(hq[q]);
+                    c_stash[u0 / 8][0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    c_stash[u0 / 8][1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
                 }
             }
-            // publish: CTA barrier, then ONE gpu-scope release (cumulative over the CTA's stores)
+            // publish: CTA barrier, then ONE gpu-scope release (cumulative over the CTA's h stores)
             tc_fence_before();
             if (warp == 2 && lane == 0) FSMG_TR(t, 6);
             named_bar_sync(1, 128 * MT);
             if (warp == 2 && lane == 0) { FSMG_TR(t, 7); __threadfence(); red_release_add(counter, 1); FSMG_TR(t, 8); }
+            if (ok) {
+                __half* gout = p.gates + r * p.G4p + j * U;
+                float* cdst = p.c + r * p.H + j * U;
+#pragma unroll
+                for (int u0 = 0; u0 < U; u0 += 8) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(gout + q * p.H + u0) = g_stash[u0 / 8][q];
+                    *reinterpret_cast<float4*>(cdst + u0) = c_stash[u0 / 8][0];
+                    *reinterpret_cast<float4*>(cdst + u0 + 4) = c_stash[u0 / 8][1];
+                }
+            }
         }
     }
     tc_fence_before();
@@ -383,7 +396,8 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     int* counter = p.counters + g;
     const int crank = (CLS > 1) ? (int)cluster_ctarank() : 0;
     constexpr uint16_t CMASK = (uint16_t)((1u << CLS) - 1u);
-    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL);
+    constexpr int STG_COLS = 5 * U;             // per row tile: gates (2U words) | c (U) | c_prev (U) | dh_out (U), staged by the epilogue warps
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL + MT * STG_COLS);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
@@ -457,18 +471,76 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 #pragma unroll
         for (int u = 0; u < U; ++u) dc_state[u] = 0.0f;
         uint32_t tf_phase = 0;
+        const int lrow = mt * 128 + quad * 32 + lane;
+        const bool ok = lrow < rows;
+        const uint32_t t_acc = tmem_base + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_stg = tmem_base + MT * NCOL + mt * STG_COLS + ((uint32_t)(quad * 32) << 16);
         for (int s = 0; s < p.T; ++s) {
             const int t = p.T - 1 - s;
-            if (t > 0) {   // pull the next processed step's stash / upstream-gradient lines towards L2
-                {
-                    const int lrow = mt * 128 + quad * 32 + lane;
-                    if (lrow < rows) {
-                        const int64_t rn = (int64_t)(t - 1) * p.N + row_base + lrow;
+            const int64_t r = (int64_t)t * p.N + row_base + lrow;
+            // The cell-backward operands of this step (forward stash + upstream gradient) do not depend on the tensor-core
+            // result: fetch them NOW, while the dgates exchange and the MMAs of this step are in flight, and park them in
+            // spare TMEM columns (TMEM as an explicit spill space: 5U words per row would not fit in registers).
+            {
+                const __half* gin = p.gates + r * p.G4p + j * U;
+                const float* cc = p.c + r * p.H + j * U;
+                const float* dho = p.dh_out + r * p.H + j * U;
+                if constexpr (U == 32) {
+                    uint32_t w[32];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) prefetch_l2(p.gates + rn * p.G4p + q * p.H + j * U);
-                        prefetch_l2(p.dh_out + rn * p.H + j * U);
-                        prefetch_l2(p.c + rn * p.H + j * U);
+                    for (int q = 0; q < 4; q += 2) {        // two gates (2 x 16 words) per 32-column store
+#pragma unroll
+                        for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+                            for (int e = 0; e < 16; e += 4) {
+                                const uint4 v = ok ? __ldcs(reinterpret_cast<const uint4*>(gin + (q + qq) * p.H + 2 * e)) : make_uint4(0, 0, 0, 0);
+                                w[qq * 16 + e] = v.x; w[qq * 16 + e + 1] = v.y; w[qq * 16 + e + 2] = v.z; w[qq * 16 + e + 3] = v.w;
+                            }
+                        tmem_st32(t_stg + q * 16, w);
                     }
+#pragma unroll
+                    for (int which = 0; which < 3; ++which) {
+                        const float* src = which == 0 ? cc : which == 1 ? cc - (int64_t)p.N * p.H : dho;
+                        const bool have = ok && !(which == 1 && t == 0);
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float4 v = have ? __ldcs(reinterpret_cast<const float4*>(src + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            w[e] = __float_as_uint(v.x); w[e + 1] = __float_as_uint(v.y); w[e + 2] = __float_as_uint(v.z); w[e + 3] = __float_as_uint(v.w);
+                        }
+                        tmem_st32(t_stg + 2 * U + which * U, w);
+                    }
+                } else {   // U == 16
+                    uint32_t w[16];
+#pragma unroll
+                    for (int q = 0; q < 4; q += 2) {
+#pragma unroll
+                        for (int qq = 0; qq < 2; ++qq)
+#pragma unroll
+                            for (int e = 0; e < 8; e += 4) {
+                                const uint4 v = ok ? __ldcs(reinterpret_cast<const uint4*>(gin + (q + qq) * p.H + 2 * e)) : make_uint4(0, 0, 0, 0);
+                                w[qq * 8 + e] = v.x; w[qq * 8 + e + 1] = v.y; w[qq * 8 + e + 2] = v.z; w[qq * 8 + e + 3] = v.w;
+                            }
+                        tmem_st16(t_stg + q * 8, w);
+                    }
+#pragma unroll
+                    for (int which = 0; which < 3; ++which) {
+                        const float* src = which == 0 ? cc : which == 1 ? cc - (int64_t)p.N * p.H : dho;
+                        const bool have = ok && !(which == 1 && t == 0);
+#pragma unroll
+                        for (int e = 0; e < 16; e += 4) {
+                            const float4 v = have ? __ldcs(reinterpret_cast<const float4*>(src + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            w[e] = __float_as_uint(v.x); w[e + 1] = __float_as_uint(v.y); w[e + 2] = __float_as_uint(v.z); w[e + 3] = __float_as_uint(v.w);
+                        }
+                        tmem_st16(t_stg + 2 * U + which * U, w);
+                    }
+                }
+                tmem_st_wait();
+                if (t > 0 && ok) {   // and pull the next processed step's lines towards L2
+                    const int64_t rn = r - p.N;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) prefetch_l2(p.gates + rn * p.G4p + q * p.H + j * U);
+                    prefetch_l2(p.dh_out + rn * p.H + j * U);
+                    if (t > 1) prefetch_l2(p.c + (rn - p.N) * p.H + j * U);
                 }
             }
             if (s > 0) {
@@ -478,58 +550,45 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
             if (warp == 2 && lane == 0) FSMG_TR(s, 5);
             {
-                const int lrow = mt * 128 + quad * 32 + lane;
-                const bool ok = lrow < rows;
-                const int64_t r = (int64_t)t * p.N + row_base + lrow;
-                const __half* gin = p.gates + r * p.G4p + j * U;
                 __half* dgo = p.dgates + r * p.G4p + j * U;
-                const uint32_t t_row = tmem_base + mt * NCOL + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int u0 = 0; u0 < U; u0 += 8) {
                     float acc[8];
+                    uint32_t gw[4][4], cw[8], pw[8], dw[8];
                     if (s > 0) {
                         uint32_t rr[8];
-                        tmem_ld8(t_row + u0, rr);
-                        tmem_ld_wait();
+                        tmem_ld8(t_acc + u0, rr);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(rr[e]);
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tmem_ld4(t_stg + q * (U / 2) + u0 / 2, gw[q]);
+                    tmem_ld8(t_stg + 2 * U + u0, cw);
+                    tmem_ld8(t_stg + 3 * U + u0, pw);
+                    tmem_ld8(t_stg + 4 * U + u0, dw);
+                    tmem_ld_wait();
                     if (ok) {
-                        __align__(16) __half hq[4][8];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(hq[q]) = *reinterpret_cast<const uint4*>(gin + q * p.H + u0);
-                        const float* dho = p.dh_out + r * p.H + j * U + u0;
-                        const float* cc = p.c + r * p.H + j * U + u0;
-                        float dh[8], cv[8], cp[8];
-                        {
-                            const float4 a = *reinterpret_cast<const float4*>(dho), b = *reinterpret_cast<const float4*>(dho + 4);
-                            dh[0] = a.x; dh[1] = a.y; dh[2] = a.z; dh[3] = a.w; dh[4] = b.x; dh[5] = b.y; dh[6] = b.z; dh[7] = b.w;
-                            const float4 c0 = *reinterpret_cast<const float4*>(cc), c1 = *reinterpret_cast<const float4*>(cc + 4);
-                            cv[0] = c0.x; cv[1] = c0.y; cv[2] = c0.z; cv[3] = c0.w; cv[4] = c1.x; cv[5] = c1.y; cv[6] = c1.z; cv[7] = c1.w;
-                            if (t > 0) {
-                                const float* cpp = cc - (int64_t)p.N * p.H;
-                                const float4 p0 = *reinterpret_cast<const float4*>(cpp), p1 = *reinterpret_cast<const float4*>(cpp + 4);
-                                cp[0] = p0.x; cp[1] = p0.y; cp[2] = p0.z; cp[3] = p0.w; cp[4] = p1.x; cp[5] = p1.y; cp[6] = p1.z; cp[7] = p1.w;
-                            } else {
-#pragma unroll
-                                for (int e = 0; e < 8; ++e) cp[e] = 0.0f;
-                            }
-                        }
                         __align__(16) __half dq[4][8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float i_ = __half2float(hq[0][e]), j_ = __half2float(hq[1][e]);
-                            const float f_ = __half2float(hq[2][e]), o_ = __half2float(hq[3][e]);
-                            const float dhv = dh[e] + acc[e];
-                            const float tcv = tanh_fast(cv[e]);
+                            const __half2 hi2 = *reinterpret_cast<const __half2*>(&gw[0][e >> 1]);
+                            const __half2 hj2 = *reinterpret_cast<const __half2*>(&gw[1][e >> 1]);
+                            const __half2 hf2 = *reinterpret_cast<const __half2*>(&gw[2][e >> 1]);
+                            const __half2 ho2 = *reinterpret_cast<const __half2*>(&gw[3][e >> 1]);
+                            const float i_ = (e & 1) ? __high2float(hi2) : __low2float(hi2);
+                            const float j_ = (e & 1) ? __high2float(hj2) : __low2float(hj2);
+                            const float f_ = (e & 1) ? __high2float(hf2) : __low2float(hf2);
+                            const float o_ = (e & 1) ? __high2float(ho2) : __low2float(ho2);
+                            const float dhv = __uint_as_float(dw[e]) + acc[e];
+                            const float tcv = tanh_fast(__uint_as_float(cw[e]));
                             const float d_o = dhv * tcv;
                             const float dc = dhv * o_ * (1.0f - tcv * tcv) + dc_state[u0 + e];
                             dq[0][e] = __float2half_rn(dc * j_ * i_ * (1.0f - i_));
                             dq[1][e] = __float2half_rn(dc * i_ * (1.0f - j_ * j_));
-                            dq[2][e] = __float2half_rn(dc * cp[e] * f_ * (1.0f - f_));
+                            dq[2][e] = __float2half_rn(dc * __uint_as_float(pw[e]) * f_ * (1.0f - f_));
                             dq[3][e] = __float2half_rn(d_o * o_ * (1.0f - o_));
                             dc_state[u0 + e] = dc * f_;
                         }
