@@ -28,8 +28,12 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Release pattern after a CTA barrier (same as CUTLASS' GenericBarrier::red_release): ONE acq_rel fence at gpu scope —
+// it is cumulative, so it also publishes what the other threads of the CTA wrote before the barrier — then a relaxed red.
+// (__threadfence() + red.release compiled to MEMBAR.SC.GPU + CCTL.IVALL + a second MEMBAR: ~3 us per step on the trace.)
 __device__ __forceinline__ void red_release_add(int* p, int v) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -343,7 +347,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             tc_fence_before();
             if (warp == 2 && lane == 0) FSMG_TR(t, 6);
             named_bar_sync(1, 128 * MT);
-            if (warp == 2 && lane == 0) { FSMG_TR(t, 7); __threadfence(); red_release_add(counter, 1); FSMG_TR(t, 8); }
+            if (warp == 2 && lane == 0) { FSMG_TR(t, 7); red_release_add(counter, 1); FSMG_TR(t, 8); }
             if (ok) {
                 __half* gout = p.gates + r * p.G4p + j * U;
                 float* cdst = p.c + r * p.H + j * U;
@@ -600,7 +604,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             tc_fence_before();
             if (warp == 2 && lane == 0) FSMG_TR(s, 6);
             named_bar_sync(1, 128 * MT);
-            if (warp == 2 && lane == 0) { FSMG_TR(s, 7); __threadfence(); red_release_add(counter, 1); FSMG_TR(s, 8); }
+            if (warp == 2 && lane == 0) { FSMG_TR(s, 7); red_release_add(counter, 1); FSMG_TR(s, 8); }
         }
     }
     tc_fence_before();
