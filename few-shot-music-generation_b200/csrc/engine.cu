@@ -83,7 +83,8 @@ struct fsmg_handle {
     // workspace carve-up
     int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *samp_ids = nullptr, *samp_out = nullptr, *samp_out2 = nullptr;
     __half *emb16 = nullptr, *Ws16 = nullptr, *WsT16 = nullptr, *xemb = nullptr, *dgates = nullptr, *dlogits = nullptr;
-    float *pre = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
+    __half* pre16 = nullptr;   // hoisted x*Wx+b, fp16 [NT, G4p]
+    float *gbuf = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
     float *lse = nullptr, *nll = nullptr, *scalars = nullptr, *dws_acc = nullptr;
     float *s_x = nullptr, *s_g = nullptr, *s_logits = nullptr;
     std::vector<float*> s_c, s_h;
@@ -150,7 +151,8 @@ static void carve(fsmg_handle* h, char* base) {
     h->Ws16 = b.take<__half>((int64_t)h->H * h->Vp);
     h->WsT16 = b.take<__half>((int64_t)h->V1 * h->Hp);
     h->xemb = b.take<__half>(NT * h->Ep);
-    h->pre = b.take<float>(NT * h->G4);
+    h->pre16 = b.take<__half>(NT * h->G4p);
+    h->gbuf = b.take<float>((int64_t)h->Nmax * h->G4);   // per-step route: recurrent contraction of one step
     h->dgates = b.take<__half>(NT * h->G4p);
     int wmax = h->E > h->H ? h->E : h->H;
     h->dact[0] = b.take<float>(NT * wmax);
@@ -280,27 +282,25 @@ static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, cudaStre
         int rc;
         {
             ProfScope ps(h, PH_INPUT_GEMM, s);
-            rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre, h->G4, 1.0f, bias), false, false, s);
+            rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre16, h->G4p, 1.0f, bias, /*c_half=*/1), false, false, s);
         }
         if (rc) return rc;
         ProfScope ps_rec(h, PH_REC_FWD, s);
         if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
             tc_recurrent_supported(h->tc, N, H)) {
-            rc = tc_lstm_forward(h->tc, h->pre, l.WhT16, l.gates, l.c, l.hs, N, T, H, h->Hp, h->G4p, s);
+            rc = tc_lstm_forward(h->tc, h->pre16, l.WhT16, l.gates, l.c, l.hs, N, T, H, h->Hp, h->G4p, s);
             LAUNCH_COUNT(h);
             if (rc) return rc;
             continue;
         }
         for (int t = 0; t < T; ++t) {
-            float* G = h->pre + (int64_t)t * N * h->G4;
             if (t > 0) {
-                rc = gemm_f16(h, mk(N, h->G4, H, l.hs + (int64_t)(t - 1) * N * h->Hp, h->Hp, l.WhT16, h->Hp, G, h->G4,
-                                    1.0f, nullptr, 0, /*accumulate=*/1), false, false, s);
+                rc = gemm_f16(h, mk(N, h->G4, H, l.hs + (int64_t)(t - 1) * N * h->Hp, h->Hp, l.WhT16, h->Hp, h->gbuf, h->G4), false, false, s);
                 if (rc) return rc;
             }
             lstm_pointwise_fwd_kernel<__half><<<cdiv((int64_t)N * H, TB), TB, 0, s>>>(
-                G, h->G4, t ? l.c + (int64_t)(t - 1) * N * H : nullptr, l.gates + (int64_t)t * N * h->G4p, h->G4p,
-                l.c + (int64_t)t * N * H, l.hs + (int64_t)t * N * h->Hp, h->Hp, N, H);
+                t ? h->gbuf : nullptr, h->G4, h->pre16 + (int64_t)t * N * h->G4p, h->G4p, t ? l.c + (int64_t)(t - 1) * N * H : nullptr,
+                l.gates + (int64_t)t * N * h->G4p, h->G4p, l.c + (int64_t)t * N * H, l.hs + (int64_t)t * N * h->Hp, h->Hp, N, H);
             LAUNCH_COUNT(h);
         }
         FSMG_LAUNCH_OK();
@@ -789,7 +789,7 @@ int fsmg_sample_greedy(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_
             // fp32 weights, fp32 FMA: argmax near-ties need fp32-grade logits
             launch_simt_gemm<float, float>(mk(n, h->G4, in_w, in, in_w, K, h->G4, h->s_g, h->G4, 1.0f, h->params + lb.b_off), false, true, s);
             launch_simt_gemm<float, float>(mk(n, h->G4, H, h->s_h[l], H, K + (int64_t)in_w * h->G4, h->G4, h->s_g, h->G4, 1.0f, nullptr, 0, 1), false, true, s);
-            lstm_pointwise_fwd_kernel<float><<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, h->s_c[l], nullptr, 0, h->s_c[l], h->s_h[l], H, n, H);
+            lstm_pointwise_fwd_kernel<float><<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, nullptr, 0, h->s_c[l], nullptr, 0, h->s_c[l], h->s_h[l], H, n, H);
             h->launches += 3;
             in = h->s_h[l];
             in_w = H;

@@ -156,7 +156,8 @@ __global__ void gather_rows_f32_kernel(const float* __restrict__ table, int64_t 
 // G: pre-activations fp32 [N, ldg] (columns [i|j|f|o], each H wide).
 // ============================================================================================
 template <typename TH>
-__global__ void lstm_pointwise_fwd_kernel(const float* __restrict__ G, int64_t ldg,
+__global__ void lstm_pointwise_fwd_kernel(const float* __restrict__ G, int64_t ldg,     // recurrent part (or the whole thing), may be null
+                                          const __half* __restrict__ pre16, int64_t ldp, // hoisted x*Wx+b in fp16, may be null
                                           const float* __restrict__ c_prev,   // [N,H] or null (zeros)
                                           __half* __restrict__ gates_out, int64_t ldgo,  // may be null
                                           float* __restrict__ c_out,          // [N,H]
@@ -164,11 +165,19 @@ __global__ void lstm_pointwise_fwd_kernel(const float* __restrict__ G, int64_t l
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)N * H) return;
     int n = (int)(idx / H), u = (int)(idx % H);
-    const float* g = G + (int64_t)n * ldg;
-    float i_ = sigmoidf_(g[u]);
-    float j_ = tanhf_(g[H + u]);
-    float f_ = sigmoidf_(g[2 * H + u] + 1.0f);
-    float o_ = sigmoidf_(g[3 * H + u]);
+    float gi = 0.0f, gj = 0.0f, gf = 0.0f, go = 0.0f;
+    if (G) {
+        const float* g = G + (int64_t)n * ldg;
+        gi = g[u]; gj = g[H + u]; gf = g[2 * H + u]; go = g[3 * H + u];
+    }
+    if (pre16) {
+        const __half* pp = pre16 + (int64_t)n * ldp;
+        gi += __half2float(pp[u]); gj += __half2float(pp[H + u]); gf += __half2float(pp[2 * H + u]); go += __half2float(pp[3 * H + u]);
+    }
+    float i_ = sigmoidf_(gi);
+    float j_ = tanhf_(gj);
+    float f_ = sigmoidf_(gf + 1.0f);
+    float o_ = sigmoidf_(go);
     float cp = c_prev ? c_prev[(int64_t)n * H + u] : 0.0f;
     float c = cp * f_ + i_ * j_;
     float h = tanhf_(c) * o_;

@@ -689,35 +689,15 @@ __global__ void __launch_bounds__(THREADS) softmax_grad_fused_kernel(__half* __r
 // there are enough small CTAs (cols/1024 x rows/ROWS) to keep >80 KB per SM in flight.
 template <int ROWS>
 __global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
-                                                                 const float2* __restrict__ part, int n_tiles,
-                                                                 const float* __restrict__ tgt, const int32_t* __restrict__ y,
-                                                                 int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
-                                                                 float* __restrict__ nll_out, float alpha, float* __restrict__ db) {
+                                                                 const float* __restrict__ lse_all, const int32_t* __restrict__ y,
+                                                                 int64_t row0, int rows, float alpha, float* __restrict__ db) {
     __shared__ float s_lse[ROWS];
     __shared__ int s_tgt[ROWS];
     const int r_begin = blockIdx.y * ROWS;
     const int n_rows = min(ROWS, rows - r_begin);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int lr = warp; lr < n_rows; lr += 4) {
-        const int row = r_begin + lr;
-        const float2* p = part + (int64_t)row * n_tiles;
-        float m = -INFINITY;
-        for (int i = lane; i < n_tiles; i += 32) m = fmaxf(m, p[i].x);
-        m = warp_max(m);
-        float s = 0.0f;
-        for (int i = lane; i < n_tiles; i += 32) s += p[i].y * __expf(p[i].x - m);
-        s = warp_sum(s);
-        if (lane == 0) {
-            const float lse = m + logf(s);
-            const int64_t r = row0 + row;
-            s_lse[lr] = lse;
-            s_tgt[lr] = y[r];
-            if (blockIdx.x == 0) {
-                if (lse_out) lse_out[r] = lse;
-                const int t = (int)(r / N), n = (int)(r % N);
-                if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[row];
-            }
-        }
+    if (threadIdx.x < n_rows) {   // the row-wise log-sum-exp was combined by lse_combine_kernel just before
+        s_lse[threadIdx.x] = lse_all[row0 + r_begin + threadIdx.x];
+        s_tgt[threadIdx.x] = y[row0 + r_begin + threadIdx.x];
     }
     __syncthreads();
     const int v0 = (blockIdx.x * 128 + threadIdx.x) * 8;
@@ -1005,8 +985,9 @@ static inline int tc_projection_post(TcContext& c, int n_part, const int32_t* y,
         tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
     } else {
         constexpr int ROWS = 32;
+        tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
         dim3 grid(cdiv(ld16, 1024), cdiv(mc, ROWS));
-        tc::softmax_grad_strip_kernel<ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, c.part, n_part, c.tgt, y, row0, mc, N, T, lse, nll_out, db_alpha, db);
+        tc::softmax_grad_strip_kernel<ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
     }
     FSMG_LAUNCH_OK();
     return 0;
