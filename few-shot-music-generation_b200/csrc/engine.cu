@@ -462,12 +462,22 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
         // dInput[NT,in] = dgates * kernel[:in,:]^T
         ProfScope ps_dx(h, PH_DX, s);
         float* dnext = h->dact[cur ^ 1];
-        rc = gemm_f16(h, mk((int)NT, l.in, h->G4, h->dgates, h->G4p, l.K16, h->G4p, dnext, l.in), false, false, s);
-        if (rc) return rc;
-        if (li == 0) {
-            scatter_emb_grad_kernel<<<(unsigned)NT, 128, 0, s>>>(dnext, l.in, h->x_ids, NT, h->E, loss_scale,
-                                                                 h->grads + h->emb_off, h->grads + h->n_params + 1);
+        GemmArgs gdx = mk((int)NT, l.in, h->G4, h->dgates, h->G4p, l.K16, h->G4p, dnext, l.in);
+        if (li == 0 && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) && tc_gemm_supported(gdx, false, false)) {
+            // layer 0: the rows of dX are the IndexedSlices values of the embedding gradient — scatter-add them (x loss_scale)
+            // into the dense gradient straight from the GEMM epilogue, accumulating the per-occurrence square norm (A.6)
+            gdx.alpha = loss_scale;
+            rc = tc_gemm_scatter(h->tc, gdx, h->x_ids, h->grads + h->emb_off, h->E, h->grads + h->n_params + 1, s);
             LAUNCH_COUNT(h);
+            if (rc) return rc;
+        } else {
+            rc = gemm_f16(h, gdx, false, false, s);
+            if (rc) return rc;
+            if (li == 0) {
+                scatter_emb_grad_kernel<<<(unsigned)NT, 128, 0, s>>>(dnext, l.in, h->x_ids, NT, h->E, loss_scale,
+                                                                     h->grads + h->emb_off, h->grads + h->n_params + 1);
+                LAUNCH_COUNT(h);
+            }
         }
         cur ^= 1;
     }

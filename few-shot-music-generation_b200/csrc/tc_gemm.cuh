@@ -158,7 +158,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 }
 
 // ---- epilogue parameter block ----------------------------------------------------------------------
-enum EpiMode { EPI_STORE = 0, EPI_LSE = 1 };
+enum EpiMode { EPI_STORE = 0, EPI_LSE = 1, EPI_SCATTER = 2 };
 
 struct EpiParams {
     // EPI_STORE
@@ -166,6 +166,8 @@ struct EpiParams {
     const float* bias; float alpha;
     int c_half, accumulate, atomic;
     int vec_ok;                         // host-checked: C base and ldc allow 16-byte (fp32) / 8-byte (fp16) row-chunk accesses
+    // EPI_SCATTER (embedding gradient): row r of the result is atomically added to C[y[row0 + r], :] (C = dense gradient table,
+    // ldc = its row length) and the squared Frobenius norm of the scattered rows is accumulated into *tgt (TF clip quirk, A.6)
     // EPI_LSE: logits = acc + bias; per (row, n-tile) online (max, sumexp); target-logit pick; optional fp16 logits
     float2* part; int n_tiles_total;    // part[row * n_tiles_total + n_blk]
     const int32_t* y; int64_t row0;     // y[row0 + row]
@@ -357,6 +359,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool row_ok = row < sh.M;
             const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
             float run_max = -INFINITY, run_sum = 0.0f;
+            float sq_acc = 0.0f;
             int tgt_col = -1;
             if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - n_blk * BN;
             // bias of every chunk of this tile, fetched before the accumulator is awaited (off the critical path)
@@ -472,6 +475,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         }
                     }
                     __syncwarp();   // staging buffer is reused by the next chunk
+                } else if (EPI == EPI_SCATTER) {
+#pragma unroll
+                    for (int c8 = 0; c8 < 8; ++c8)
+                        st4[lane * 8 + (c8 ^ (lane & 7))] =
+                            make_float4(ep.alpha * __uint_as_float(r[4 * c8]), ep.alpha * __uint_as_float(r[4 * c8 + 1]),
+                                        ep.alpha * __uint_as_float(r[4 * c8 + 2]), ep.alpha * __uint_as_float(r[4 * c8 + 3]));
+                    __syncwarp();
+                    const int c8 = lane & 7;
+                    const int colv = col0 + 4 * c8;
+                    const bool vec = full && ep.vec_ok;
+                    float* C = reinterpret_cast<float*>(ep.C);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int rr = 4 * k + (lane >> 3);
+                        const int grow = row_w0 + rr;
+                        if (grow >= sh.M) continue;
+                        const float4 v = st4[rr * 8 + (c8 ^ (rr & 7))];
+                        float* dst = C + (int64_t)ep.y[ep.row0 + grow] * ep.ldc + colv;
+                        if (vec) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                            sq_acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+                        } else {
+                            const float e4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (colv + e < sh.N) { atomicAdd(dst + e, e4[e]); sq_acc += e4[e] * e4[e]; }
+                        }
+                    }
+                    __syncwarp();
                 } else {  // EPI_LSE
                     // bias for this chunk: one coalesced load, then broadcast by shuffle
                     float v[32];
@@ -545,6 +577,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
             }
             if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk * 2 + half] = make_float2(run_max, run_sum);
+            if (EPI == EPI_SCATTER) {
+                sq_acc = warp_sum(sq_acc);
+                if (lane == 0 && sq_acc != 0.0f) atomicAdd(ep.tgt, sq_acc);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // NUM_EPI_WARPS arrivals free the accumulator stage
@@ -799,6 +835,8 @@ static inline int tc_init(TcContext& c) {
     FSMG_SET_SMEM(128, tc::EPI_STORE, false, false);
     FSMG_SET_SMEM(128, tc::EPI_STORE, true, true);
     FSMG_SET_SMEM(256, tc::EPI_LSE, false, false);
+    FSMG_SET_SMEM(256, tc::EPI_SCATTER, false, false);
+    FSMG_SET_SMEM(128, tc::EPI_SCATTER, false, false);
     FSMG_SET_SMEM(128, tc::EPI_LSE, false, false);
 #undef FSMG_SET_SMEM
     c.ready = true;
@@ -907,7 +945,7 @@ static inline int tc_launch(const TcContext& c, const TcPlan& p, const CUtensorM
     (p.cl == 2 ? tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 2>, p, tc::SmemLayout<BN>::TOTAL, ma, mb, ep, s)       \
                : tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 1>, p, tc::SmemLayout<BN>::TOTAL, ma, mb, ep, s))
     int rc = 0;
-    if constexpr (EPI == tc::EPI_LSE) {
+    if constexpr (EPI == tc::EPI_LSE || EPI == tc::EPI_SCATTER) {
         rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
     } else {
         if (!mn) rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
@@ -950,6 +988,22 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
     int rc = tc_make_maps(c, g, a_mn, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;
     return tc_launch<tc::EPI_STORE>(c, p, ma, mb, a_mn, ep, s);
+}
+
+// dX[r,:] = A[r,:] * B^T scattered into table[ids[r], :] (+= alpha * dX[r,:]) with the per-occurrence square norm: the embedding
+// gradient of the hot path (IndexedSlices densification, reference lstm_baseline.py:83-85) without materialising dX
+static inline int tc_gemm_scatter(TcContext& c, const GemmArgs& g, const int32_t* ids, float* table, int64_t ld_table, float* occ_sq,
+                                  cudaStream_t s) {
+    if (!c.ready) return set_error(-3, "tcgen05 context not initialised");
+    TcPlan p = tc_plan(c, g.M, g.N, g.K, false);
+    tc::EpiParams ep;
+    memset(&ep, 0, sizeof ep);
+    ep.C = table; ep.ldc = ld_table; ep.alpha = g.alpha; ep.y = ids; ep.row0 = 0; ep.tgt = occ_sq;
+    ep.vec_ok = ((reinterpret_cast<uintptr_t>(table) & 15) == 0 && (ld_table % 4) == 0) ? 1 : 0;
+    CUtensorMap ma, mb;
+    int rc = tc_make_maps(c, g, false, p.bn, p.cl, &ma, &mb);
+    if (rc) return rc;
+    return tc_launch<tc::EPI_SCATTER>(c, p, ma, mb, false, ep, s);
 }
 
 // ---- projection forward: logits tile -> online LSE partials (+ fp16 logits when training) -------------

@@ -19,5 +19,7 @@ def test_two_gpu_data_parallel_step_matches_single_process(built_lib):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                           "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), str(worker)],
                          capture_output=True, text=True, timeout=600)
+    (Path(__file__).resolve().parents[1] / "gpurun_out").mkdir(exist_ok=True)
+    (Path(__file__).resolve().parents[1] / "gpurun_out" / "dp_worker_last.log").write_text(out.stdout[-20000:] + "\n==== stderr ====\n" + out.stderr[-20000:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "DP_OK" in out.stdout
