@@ -903,11 +903,11 @@ static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow
     sh.streamk = 0;
     sh.units_per_cluster = 0;
     if (allow_split && c.streamk) {
-        // wave quantisation of the plain schedule; below 90 % switch to stream-K (perfectly balanced k-block ranges)
+        // wave quantisation of the plain schedule; below 80 % switch to stream-K (perfectly balanced k-block ranges)
         const int rounds = cdiv(total, slots);
         const double eff = (double)total / ((double)rounds * slots);
         const int64_t units = (int64_t)tiles * sh.kb_total;
-        if (eff < 0.90 && units >= 16) {
+        if (eff < 0.80 && units >= 16) {
             int ncl = slots;
             int upc = (int)cdiv(units, ncl);
             if (upc < 8) { upc = 8; ncl = (int)cdiv(units, upc); }
@@ -1038,7 +1038,7 @@ static inline int tc_projection_post(TcContext& c, int n_part, const int32_t* y,
     if (!logits16) {
         tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
     } else {
-        constexpr int ROWS = 32;
+        constexpr int ROWS = 128;   // rows per strip: one atomicAdd per column per 128 rows for the bias gradient
         tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
         dim3 grid(cdiv(ld16, 1024), cdiv(mc, ROWS));
         tc::softmax_grad_strip_kernel<ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
