@@ -113,6 +113,38 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
                  "h"(mask)
                  : "memory");
 }
+// ---- cta_group::2 (two SMs cooperate on one 256-row MMA; issued by the leader CTA of the pair only) ---------------------
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -153,6 +185,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // Instruction descriptor (kind::f16): c_format F32 (bits 4-5 = 1), a/b format F16 (0), a_major bit 15,
 // b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bits 17-22, M>>4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n) {   // K-major operands, explicit M (256 for cta_group::2)
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
     return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -795,6 +830,7 @@ struct TcContext {
     int enabled = 1;
     int cluster = 2;           // CTAs per cluster of the GEMM core (2 = B-tile multicast pairs, 1 = no clusters)
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
+    int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
 };
 
@@ -815,6 +851,8 @@ static inline int tc_init(TcContext& c) {
     c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
     const char* envs = getenv("FSMG_STREAMK");
     c.streamk = envs ? atoi(envs) : 1;
+    const char* envp = getenv("FSMG_LSTM_PAIR");
+    c.lstm_pair = envp ? atoi(envp) : 0;
     const char* envl = getenv("FSMG_LSTM_CLUSTER");
     c.lstm_cluster = envl ? atoi(envl) : 1;
     int dev = 0;

@@ -126,7 +126,7 @@ __host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 
 // =====================================================================================================
 // CLS > 1: the CLS CTAs of a thread-block cluster serve the same group; each fetches every CLS-th K chunk of the
 // exchanged operand and TMA-multicasts it to all of them (L2 -> SMEM traffic / CLS).
-template <int U, int MT, int CLS>
+template <int U, int MT, int CLS, bool PAIR>
 __global__ void __launch_bounds__(lstm_threads(MT), 1)
 lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, LstmParams p) {
     constexpr int NCOL = 4 * U;                 // accumulator columns per row tile (UMMA N)
@@ -369,8 +369,11 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
 //   dh = dh_out[t] + dh_rec ; do = dh*tanh(c) ; dc = dh*o*(1-tanh(c)^2) + dc_next
 //   dgi = dc*j*i(1-i) ; dgj = dc*i*(1-j^2) ; dgf = dc*c_prev*f(1-f) ; dgo = do*o(1-o) ; dc_next' = dc*f
 // =====================================================================================================
-template <int U, int MT, int CLS>
-__global__ void __launch_bounds__(lstm_threads(MT), 1)
+// PAIR: the two CTAs of a cluster form one cta_group::2 MMA of 256 rows: each CTA streams only ITS half of the group's rows of
+// the exchanged operand (the measured bottleneck is per-SM operand ingest) and contributes its own resident weight slice as half of
+// B; each CTA's epilogue then owns (its rows) x (both CTAs' units), one warp quartet per unit slice.
+template <int U, int MT, int CLS, bool PAIR>
+__global__ void __launch_bounds__(lstm_threads(PAIR ? 2 : MT), 1)
 lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dg, LstmParams p) {
     constexpr int NCOL = U;
     constexpr int CHUNK_W = U * 128;
@@ -388,16 +391,22 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     uint64_t* w_bar = bars + 16;
     uint64_t* tmem_full = bars + 17;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    uint64_t* peer_full = bars + 20;            // [8] PAIR, leader only: the peer CTA's stage holds its half of the rows
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
-    const int row_base = p.row_offset + g * p.rows_per_group;
-    const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);
+    static_assert(!PAIR || (MT == 1 && CLS == 1), "PAIR mode: one row tile per CTA, the cluster is the pair");
+    constexpr int NQ = PAIR ? 2 : MT;           // epilogue warp quartets: row tiles (plain) or unit slices (PAIR)
+    const int prank = PAIR ? (int)cluster_ctarank() : 0;
+    const int group_row0 = p.row_offset + g * p.rows_per_group;
+    const int group_rows = min(p.rows_per_group, p.row_offset + p.n_rows - group_row0);
+    const int row_base = PAIR ? group_row0 + prank * p.box_rows : group_row0;          // first row this CTA streams / owns
+    const int rows = PAIR ? max(0, min(p.box_rows, group_rows - prank * p.box_rows)) : group_rows;
     int* counter = p.counters + g;
     const int crank = (CLS > 1) ? (int)cluster_ctarank() : 0;
     constexpr uint16_t CMASK = (uint16_t)((1u << CLS) - 1u);
     constexpr int STG_COLS = 5 * U;             // per row tile: gates (2U words) | c (U) | c_prev (U) | dh_out (U), staged by the epilogue warps
-    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(MT * NCOL + MT * STG_COLS);
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
@@ -405,12 +414,13 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CLS); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
+        if (PAIR) for (int i = 0; i < STAGES; ++i) mbar_init(&peer_full[i], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
-    if (CLS > 1) cluster_sync_all();
+    if (CLS > 1 || PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -436,45 +446,69 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(NCOL, false, false);
+        if (lane == 0 && PAIR && prank == 1) {
+            // peer CTA: no MMA issue; relay "my half of the rows has landed" to the leader, stage by stage.  Its resident weight
+            // slice (half of B) must be complete before the first relay: wait for it here.
+            mbar_wait(w_bar, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int s = 1; s < p.T; ++s)
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    mbar_arrive_remote(&peer_full[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+        } else if (lane == 0) {
+            constexpr uint32_t idesc = PAIR ? make_idesc_m(256, 2 * NCOL) : make_idesc(NCOL, false, false);
             mbar_wait(w_bar, 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
             for (int s = 1; s < p.T; ++s) {
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (PAIR) mbar_wait(&peer_full[stage], phase);
                     if (kc == 0) FSMG_TR(s, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
+                    if (PAIR) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
+                            const uint64_t a_desc = make_smem_desc(sa + k * 32, 16, 1024);
                             const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
-                            umma_f16(tmem_base + mt * NCOL, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_f16_2sm(tmem_base, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                         }
+                        umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);
+                    } else {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
+                                const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
+                                umma_f16(tmem_base + mt * NCOL, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            }
+                        }
+                        if (CLS > 1) umma_commit_mc(&empty_bar[stage], CMASK); else umma_commit(&empty_bar[stage]);
                     }
-                    if (CLS > 1) umma_commit_mc(&empty_bar[stage], CMASK); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tmem_full);
+                if (PAIR) umma_commit_2sm_mc(tmem_full, (uint16_t)0x3); else umma_commit(tmem_full);
                 FSMG_TR(s, 3);
             }
         }
     } else {
         const int quad = warp & 3;
-        const int mt = (warp - 2) >> 2;
+        const int q_idx = (warp - 2) >> 2;                 // quartet: row tile (plain) or unit slice of the pair (PAIR)
+        const int mt = PAIR ? 0 : q_idx;
+        const int ju = PAIR ? (j & ~1) + q_idx : j;        // unit slice whose gates this quartet differentiates
         float dc_state[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) dc_state[u] = 0.0f;
         uint32_t tf_phase = 0;
         const int lrow = mt * 128 + quad * 32 + lane;
         const bool ok = lrow < rows;
-        const uint32_t t_acc = tmem_base + mt * NCOL + ((uint32_t)(quad * 32) << 16);
-        const uint32_t t_stg = tmem_base + MT * NCOL + mt * STG_COLS + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_acc = tmem_base + q_idx * NCOL + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_stg = tmem_base + NQ * NCOL + q_idx * STG_COLS + ((uint32_t)(quad * 32) << 16);
         for (int s = 0; s < p.T; ++s) {
             const int t = p.T - 1 - s;
             const int64_t r = (int64_t)t * p.N + row_base + lrow;
@@ -482,9 +516,9 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             // result: fetch them NOW, while the dgates exchange and the MMAs of this step are in flight, and park them in
             // spare TMEM columns (TMEM as an explicit spill space: 5U words per row would not fit in registers).
             {
-                const __half* gin = p.gates + r * p.G4p + j * U;
-                const float* cc = p.c + r * p.H + j * U;
-                const float* dho = p.dh_out + r * p.H + j * U;
+                const __half* gin = p.gates + r * p.G4p + ju * U;
+                const float* cc = p.c + r * p.H + ju * U;
+                const float* dho = p.dh_out + r * p.H + ju * U;
                 if constexpr (U == 32) {
                     uint32_t w[32];
 #pragma unroll
@@ -538,9 +572,9 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 if (t > 0 && ok) {   // and pull the next processed step's lines towards L2
                     const int64_t rn = r - p.N;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) prefetch_l2(p.gates + rn * p.G4p + q * p.H + j * U);
-                    prefetch_l2(p.dh_out + rn * p.H + j * U);
-                    if (t > 1) prefetch_l2(p.c + (rn - p.N) * p.H + j * U);
+                    for (int q = 0; q < 4; ++q) prefetch_l2(p.gates + rn * p.G4p + q * p.H + ju * U);
+                    prefetch_l2(p.dh_out + rn * p.H + ju * U);
+                    if (t > 1) prefetch_l2(p.c + (rn - p.N) * p.H + ju * U);
                 }
             }
             if (s > 0) {
@@ -550,7 +584,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
             if (warp == 2 && lane == 0) FSMG_TR(s, 5);
             {
-                __half* dgo = p.dgates + r * p.G4p + j * U;
+                __half* dgo = p.dgates + r * p.G4p + ju * U;
 #pragma unroll
                 for (int u0 = 0; u0 < U; u0 += 8) {
                     float acc[8];
@@ -599,14 +633,14 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
             tc_fence_before();
             if (warp == 2 && lane == 0) FSMG_TR(s, 6);
-            named_bar_sync(1, 128 * MT);
+            named_bar_sync(1, 128 * NQ);
             if (warp == 2 && lane == 0) { FSMG_TR(s, 7); red_release_add(counter, 1); FSMG_TR(s, 8); }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (CLS > 1) cluster_sync_all();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CLS > 1 || PAIR) cluster_sync_all();
+    if (warp == 1) { if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 }  // namespace tc
@@ -629,10 +663,10 @@ static inline void lstm_ring(int w_bytes, int box_rows, int mt, int* stage_bytes
 
 struct LstmPlan {
     int U, MT, C, G, rows_per_group, box_rows, rows_per_launch, cls;
-    bool ok;
+    bool ok, pair;
 };
 
-static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, int cls_req = -1) {
+static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, bool want_pair = false, int cls_req = -1) {
     LstmPlan pl;
     memset(&pl, 0, sizeof pl);
     pl.ok = false;
@@ -657,6 +691,12 @@ static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, int cls_req =
     pl.rows_per_group = mg;
     pl.box_rows = mg;
     pl.MT = mg > 128 ? 2 : 1;
+    pl.pair = want_pair && (pl.C % 2 == 0) && mg > 8;
+    if (pl.pair) {            // cta_group::2: each CTA of a pair streams half of the group's rows
+        pl.cls = 1;
+        pl.MT = 1;
+        pl.box_rows = (int)round_up(cdiv(mg, 2), 8);
+    }
     pl.rows_per_launch = gmax * mg;
     pl.G = gmax;
     pl.ok = true;
@@ -697,25 +737,30 @@ static inline int lstm_launch(K kernel, int grid, int threads, int cls, int smem
     return 0;
 }
 
-#define FSMG_LSTM_DISPATCH(KERNEL, RC)                                                                            \
+#define FSMG_LSTM_GO(KERNEL, UU, MM, CC, PP) RC_ = lstm_launch(tc::KERNEL<UU, MM, CC, PP>, G * pl.C, tc::lstm_threads((PP) ? 2 : (MM)), (PP) ? 2 : (CC), smem, mw, mx, p, s)
+#define FSMG_LSTM_DISPATCH(KERNEL, RC, ALLOW_PAIR)                                                                \
     do {                                                                                                          \
-        if (pl.U == 32 && pl.MT == 2) {                                                                           \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 2, 4>, G * pl.C, tc::lstm_threads(2), 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 2, 2>, G * pl.C, tc::lstm_threads(2), 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<32, 2, 1>, G * pl.C, tc::lstm_threads(2), 1, smem, mw, mx, p, s);                         \
+        int RC_ = 0;                                                                                              \
+        if (pl.pair && (ALLOW_PAIR)) {                                                                            \
+            if (pl.U == 32) FSMG_LSTM_GO(KERNEL, 32, 1, 1, true); else FSMG_LSTM_GO(KERNEL, 16, 1, 1, true);      \
+        } else if (pl.U == 32 && pl.MT == 2) {                                                                    \
+            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 2, 4, false);                                               \
+            else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 32, 2, 2, false);                                          \
+            else FSMG_LSTM_GO(KERNEL, 32, 2, 1, false);                                                           \
         } else if (pl.U == 32) {                                                                                  \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<32, 1, 4>, G * pl.C, tc::lstm_threads(1), 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<32, 1, 2>, G * pl.C, tc::lstm_threads(1), 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<32, 1, 1>, G * pl.C, tc::lstm_threads(1), 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 1, 4, false);                                               \
+            else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 32, 1, 2, false);                                          \
+            else FSMG_LSTM_GO(KERNEL, 32, 1, 1, false);                                                           \
         } else if (pl.MT == 2) {                                                                                  \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 2, 4>, G * pl.C, tc::lstm_threads(2), 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 2, 2>, G * pl.C, tc::lstm_threads(2), 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<16, 2, 1>, G * pl.C, tc::lstm_threads(2), 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 16, 2, 4, false);                                               \
+            else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 16, 2, 2, false);                                          \
+            else FSMG_LSTM_GO(KERNEL, 16, 2, 1, false);                                                           \
         } else {                                                                                                  \
-            if (pl.cls == 4) RC = lstm_launch(tc::KERNEL<16, 1, 4>, G * pl.C, tc::lstm_threads(1), 4, smem, mw, mx, p, s);             \
-            else if (pl.cls == 2) RC = lstm_launch(tc::KERNEL<16, 1, 2>, G * pl.C, tc::lstm_threads(1), 2, smem, mw, mx, p, s);        \
-            else RC = lstm_launch(tc::KERNEL<16, 1, 1>, G * pl.C, tc::lstm_threads(1), 1, smem, mw, mx, p, s);                         \
+            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 16, 1, 4, false);                                               \
+            else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 16, 1, 2, false);                                          \
+            else FSMG_LSTM_GO(KERNEL, 16, 1, 1, false);                                                           \
         }                                                                                                         \
+        RC = RC_;                                                                                                 \
     } while (0)
 
 static inline void lstm_trace_dump(TcContext& c, const char* what, cudaStream_t s) {
@@ -764,7 +809,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
         const CUtensorMap& mx = mh;
         const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
         if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
-        FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc);
+        FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc, false);
         if (trace && !rc) lstm_trace_dump(c, "lstm_fwd_persistent", s);
         if (rc) return rc;
     }
@@ -774,7 +819,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
 // dh_out [T*N,H] fp32, Wh_rows = kernel[in:, :] fp16 [H, G4p] -> dgates [T*N,G4p]
 static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __half* Wh_rows, const __half* gates, const float* cbuf,
                                    __half* dgates, int N, int T, int H, int G4p, cudaStream_t s) {
-    LstmPlan pl = lstm_plan(c, N, H);
+    LstmPlan pl = lstm_plan(c, N, H, c.lstm_pair != 0);
     if (!pl.ok) return set_error(-1, "persistent LSTM: unsupported shape N=%d H=%d", N, H);
     CUtensorMap mw, md;
     int rc = make_map_f16(c, &mw, Wh_rows, (uint64_t)4 * H, (uint64_t)H, (uint64_t)G4p, 64, (uint32_t)pl.U);
@@ -796,7 +841,7 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         const CUtensorMap& mx = md;
         const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
         if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
-        FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc);
+        FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc, true);
         if (trace && !rc) lstm_trace_dump(c, "lstm_bwd_persistent", s);
         if (rc) return rc;
     }
