@@ -127,7 +127,7 @@ __host__ __device__ constexpr uint32_t tmem_cols_pow2(int n) { return n <= 32 ? 
 // CLS > 1: the CLS CTAs of a thread-block cluster serve the same group; each fetches every CLS-th K chunk of the
 // exchanged operand and TMA-multicasts it to all of them (L2 -> SMEM traffic / CLS).
 template <int U, int MT, int CLS, bool PAIR>
-__global__ void __launch_bounds__(lstm_threads(MT), 1)
+__global__ void __launch_bounds__(lstm_threads(PAIR ? 2 : MT), 1)
 lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, LstmParams p) {
     constexpr int NCOL = 4 * U;                 // accumulator columns per row tile (UMMA N)
     constexpr int CHUNK_W = NCOL * 128;         // bytes of the weight slice per 64-wide K chunk
@@ -148,15 +148,21 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                                                 // Two barriers (not one) so the epilogue can never run two phases ahead of the MMA
                                                 // thread (e.g. while it still waits for the one-time weight load).
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+    uint64_t* peer_full = bars + 22;            // [8] PAIR, leader only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
-    const int row_base = p.row_offset + g * p.rows_per_group;                       // first sequence of the group
-    const int rows = min(p.rows_per_group, p.row_offset + p.n_rows - row_base);     // sequences present (>= 1)
+    static_assert(!PAIR || (MT == 1 && CLS == 1), "PAIR mode: one row tile per CTA, the cluster is the pair");
+    constexpr int NQ = PAIR ? 2 : MT;           // epilogue warp quartets: row tiles (plain) or unit slices (PAIR)
+    const int prank = PAIR ? (int)cluster_ctarank() : 0;
+    const int group_row0 = p.row_offset + g * p.rows_per_group;                      // first sequence of the group
+    const int group_rows = min(p.rows_per_group, p.row_offset + p.n_rows - group_row0);
+    const int row_base = PAIR ? group_row0 + prank * p.box_rows : group_row0;          // first row this CTA streams / owns
+    const int rows = PAIR ? max(0, min(p.box_rows, group_rows - prank * p.box_rows)) : group_rows;
     int* counter = p.counters + g;
     const int crank = (CLS > 1) ? (int)cluster_ctarank() : 0;
     constexpr uint16_t CMASK = (uint16_t)((1u << CLS) - 1u);
-    constexpr int BUF_COLS = MT * NCOL;               // one accumulator buffer; two buffers alternate per step
+    constexpr int BUF_COLS = NQ * NCOL;               // one accumulator buffer; two buffers alternate per step
     constexpr uint32_t TMEM_COLS = tmem_cols_pow2(2 * BUF_COLS);
 
     if (warp == 0 && lane == 0) {
@@ -165,14 +171,15 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CLS); }
         mbar_init(w_bar, 1);
         mbar_init(tmem_full, 1);
-        mbar_init(&pre_ready[0], 4 * MT);
-        mbar_init(&pre_ready[1], 4 * MT);
+        mbar_init(&pre_ready[0], PAIR ? 16 : 4 * MT);   // PAIR: the leader's barrier collects both CTAs' 8 epilogue warps
+        mbar_init(&pre_ready[1], PAIR ? 16 : 4 * MT);
+        if (PAIR) for (int i = 0; i < STAGES; ++i) mbar_init(&peer_full[i], 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 1) { if (PAIR) tmem_alloc_2sm(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
-    if (CLS > 1) cluster_sync_all();
+    if (CLS > 1 || PAIR) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -201,8 +208,18 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(NCOL, false, false);
+        if (lane == 0 && PAIR && prank == 1) {
+            // peer CTA: relay "my half of the rows has landed" (and, first, "my weight slice is resident") to the leader
+            mbar_wait(w_bar, 0);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 1; t < p.T; ++t)
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full_bar[stage], phase);
+                    mbar_arrive_remote(&peer_full[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+        } else if (lane == 0) {
+            constexpr uint32_t idesc = PAIR ? make_idesc_m(256, 2 * NCOL) : make_idesc(NCOL, false, false);
             mbar_wait(w_bar, 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
@@ -216,30 +233,43 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 const uint32_t d_buf = tmem_base + (uint32_t)((t & 1) * BUF_COLS);
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (PAIR) mbar_wait(&peer_full[stage], phase);
                     if (kc == 0) FSMG_TR(t, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
-#pragma unroll
-                    for (int mt = 0; mt < MT; ++mt) {
+                    if (PAIR) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
+                            const uint64_t a_desc = make_smem_desc(sa + k * 32, 16, 1024);
                             const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
-                            umma_f16(d_buf + mt * NCOL, a_desc, b_desc, idesc, 1u);
+                            umma_f16_2sm(d_buf, a_desc, b_desc, idesc, 1u);
                         }
+                        umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);
+                    } else {
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t a_desc = make_smem_desc(sa + mt * 128 * 128 + k * 32, 16, 1024);
+                                const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
+                                umma_f16(d_buf + mt * NCOL, a_desc, b_desc, idesc, 1u);
+                            }
+                        }
+                        if (CLS > 1) umma_commit_mc(&empty_bar[stage], CMASK); else umma_commit(&empty_bar[stage]);
                     }
-                    if (CLS > 1) umma_commit_mc(&empty_bar[stage], CMASK); else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tmem_full);
+                if (PAIR) umma_commit_2sm_mc(tmem_full, (uint16_t)0x3); else umma_commit(tmem_full);
                 FSMG_TR(t, 3);
             }
         }
     } else {
         // ===== epilogue: thread <-> (row tile mt, TMEM lane); the cell state c stays in registers for all T steps
         const int quad = warp & 3;
-        const int mt = (warp - 2) >> 2;          // row tile owned by this warp quartet
+        const int q_idx = (warp - 2) >> 2;       // quartet: row tile (plain) or unit slice of the pair (PAIR)
+        const int mt = PAIR ? 0 : q_idx;
+        const int ju = PAIR ? (j & ~1) + q_idx : j;
         float c_state[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) c_state[u] = 0.0f;
@@ -249,8 +279,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             {
                 const int lrow = mt * 128 + quad * 32 + lane;
                 const bool ok = lrow < rows;
-                const __half* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * p.G4p + j * U;
-                const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+                const __half* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * p.G4p + ju * U;
+                const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + q_idx * NCOL + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t rr[U];
@@ -277,13 +307,13 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 stage_pre(t + 1);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&pre_ready[(t + 1) & 1]);
+                if (lane == 0) { if (PAIR && prank == 1) mbar_arrive_remote(&pre_ready[(t + 1) & 1], 0); else mbar_arrive(&pre_ready[(t + 1) & 1]); }
                 if (warp == 2 && lane == 0) FSMG_TR(t, 4);
                 if (t + 2 < p.T) {   // and pull step t+2's lines towards L2
                     {
                         const int lrow = mt * 128 + quad * 32 + lane;
                         if (lrow < rows) {
-                            const __half* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * p.G4p + j * U;
+                            const __half* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * p.G4p + ju * U;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
                         }
@@ -304,7 +334,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             uint4 g_stash[U / 8][4];
             float4 c_stash[U / 8][2];
             {
-                const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + mt * NCOL + ((uint32_t)(quad * 32) << 16);
+                const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + q_idx * NCOL + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int u0 = 0; u0 < U; u0 += 8) {
                     float acc[4][8];
@@ -332,7 +362,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                         hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
                         hh[e] = __float2half_rn(tanh_fast(cv) * o_);
                     }
-                    if (ok) *reinterpret_cast<uint4*>(p.hs + r * p.Hp + j * U + u0) = *reinterpret_cast<uint4*>(hh);
+                    if (ok) *reinterpret_cast<uint4*>(p.hs + r * p.Hp + ju * U + u0) = *reinterpret_cast<uint4*>(hh);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) g_stash[u0 / 8][q] = *reinterpret_cast<uint4*>(hq[q]);
                     c_stash[u0 / 8][0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
@@ -342,11 +372,11 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             // publish: CTA barrier, then ONE gpu-scope release (cumulative over the CTA's h stores)
             tc_fence_before();
             if (warp == 2 && lane == 0) FSMG_TR(t, 6);
-            named_bar_sync(1, 128 * MT);
+            named_bar_sync(1, 128 * NQ);
             if (warp == 2 && lane == 0) { FSMG_TR(t, 7); red_release_add(counter, 1); FSMG_TR(t, 8); }
             if (ok) {
-                __half* gout = p.gates + r * p.G4p + j * U;
-                float* cdst = p.c + r * p.H + j * U;
+                __half* gout = p.gates + r * p.G4p + ju * U;
+                float* cdst = p.c + r * p.H + ju * U;
 #pragma unroll
                 for (int u0 = 0; u0 < U; u0 += 8) {
 #pragma unroll
@@ -359,8 +389,8 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     }
     tc_fence_before();
     __syncthreads();
-    if (CLS > 1) cluster_sync_all();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CLS > 1 || PAIR) cluster_sync_all();
+    if (warp == 1) { if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // =====================================================================================================
@@ -787,7 +817,7 @@ static inline bool tc_recurrent_supported(TcContext& c, int N, int H) {
 // pre [T*N,4H] fp32, WhT16 [4H,Hp] fp16 -> gates [T*N,G4p], c [T*N,H], hs [T*N,Hp]
 static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half* WhT16, __half* gates, float* cbuf, __half* hs, int N,
                                   int T, int H, int Hp, int G4p, cudaStream_t s) {
-    LstmPlan pl = lstm_plan(c, N, H);
+    LstmPlan pl = lstm_plan(c, N, H, (c.lstm_pair & 2) != 0);
     if (!pl.ok) return set_error(-1, "persistent LSTM: unsupported shape N=%d H=%d", N, H);
     CUtensorMap mw, mh;
     int rc = make_map_f16(c, &mw, WhT16, (uint64_t)H, (uint64_t)4 * H, (uint64_t)Hp, 64, (uint32_t)pl.U);
@@ -809,7 +839,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
         const CUtensorMap& mx = mh;
         const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
         if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
-        FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc, false);
+        FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc, true);
         if (trace && !rc) lstm_trace_dump(c, "lstm_fwd_persistent", s);
         if (rc) return rc;
     }
@@ -819,7 +849,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
 // dh_out [T*N,H] fp32, Wh_rows = kernel[in:, :] fp16 [H, G4p] -> dgates [T*N,G4p]
 static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __half* Wh_rows, const __half* gates, const float* cbuf,
                                    __half* dgates, int N, int T, int H, int G4p, cudaStream_t s) {
-    LstmPlan pl = lstm_plan(c, N, H, c.lstm_pair != 0);
+    LstmPlan pl = lstm_plan(c, N, H, (c.lstm_pair & 1) != 0);
     if (!pl.ok) return set_error(-1, "persistent LSTM: unsupported shape N=%d H=%d", N, H);
     CUtensorMap mw, md;
     int rc = make_map_f16(c, &mw, Wh_rows, (uint64_t)4 * H, (uint64_t)H, (uint64_t)G4p, 64, (uint32_t)pl.U);
