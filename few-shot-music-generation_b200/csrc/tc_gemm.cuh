@@ -543,6 +543,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     // bias for this chunk: one coalesced load, then broadcast by shuffle
                     float v[32];
                     float cmax = -INFINITY;
+                    float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                     if (full) {   // warp-uniform fast path: no per-element column guards
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -551,8 +552,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                             v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
                             v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-                            cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
+                            cm4[(j >> 2) & 3] = fmaxf(cm4[(j >> 2) & 3], fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
                         }
+                        cmax = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
@@ -573,9 +575,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     const float nmax = fmaxf(run_max, cmax);
                     const float nmax_l2 = nmax * 1.4426950408889634f;
-                    float sacc = 0.0f;
+                    float sa0 = 0.0f, sa1 = 0.0f, sa2 = 0.0f, sa3 = 0.0f;   // four independent chains: the 32-long serial FADD chain was latency-bound
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sacc += exp2f(fmaf(v[j], 1.4426950408889634f, -nmax_l2));   // one FFMA + MUFU.EX2
+                    for (int j = 0; j < 32; j += 4) {
+                        sa0 += exp2f(fmaf(v[j], 1.4426950408889634f, -nmax_l2));          // one FFMA + MUFU.EX2 per logit
+                        sa1 += exp2f(fmaf(v[j + 1], 1.4426950408889634f, -nmax_l2));
+                        sa2 += exp2f(fmaf(v[j + 2], 1.4426950408889634f, -nmax_l2));
+                        sa3 += exp2f(fmaf(v[j + 3], 1.4426950408889634f, -nmax_l2));
+                    }
+                    const float sacc = (sa0 + sa1) + (sa2 + sa3);
                     run_sum = run_sum * __expf(run_max - nmax) + sacc;
                     run_max = nmax;
                     if (ep.logits16) {

@@ -52,6 +52,18 @@ __device__ __forceinline__ void tma_load_3d_mc(void* dst, const CUtensorMap* map
         "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// cta_group::2 flavour: the data lands in THIS CTA's smem, the complete_tx goes to the mbarrier at the same offset in CTA 0 (the
+// MMA-issuing leader of the pair) — no software relay between the peer's TMA completion and the leader's MMA thread
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar_local) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 rb;\n"
+        "mapa.shared::cluster.u32 rb, %2, 0;\n"
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [rb];\n"
+        "}\n" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar_local)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // 32 lanes x 8 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -199,6 +211,12 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 fence_proxy_async_all();                    // generic-proxy writes -> async-proxy (TMA) reads
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (PAIR) {   // the leader's barrier collects both halves: it expects 2 x box bytes, the peer only issues its load
+                        if (prank == 0) mbar_expect_tx(&full_bar[stage], 2 * box_bytes);
+                        tma_load_3d_2sm(sA + stage * STAGE_BYTES, &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], box_bytes);
                     if (CLS == 1) tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kc * 64, row_base, t - 1, &full_bar[stage]);
                     else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_h, kc * 64, row_base, t - 1, &full_bar[stage], CMASK);
@@ -209,18 +227,13 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         }
     } else if (warp == 1) {
         if (lane == 0 && PAIR && prank == 1) {
-            // peer CTA: relay "my half of the rows has landed" (and, first, "my weight slice is resident") to the leader
+            // peer CTA: no MMA issue.  Tell the leader once that this CTA's resident weight slice (half of B) has landed.
             mbar_wait(w_bar, 0);
-            int stage = 0; uint32_t phase = 0;
-            for (int t = 1; t < p.T; ++t)
-                for (int kc = 0; kc < KC; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    mbar_arrive_remote(&peer_full[stage], 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
+            mbar_arrive_remote(&peer_full[0], 0);
         } else if (lane == 0) {
             constexpr uint32_t idesc = PAIR ? make_idesc_m(256, 2 * NCOL) : make_idesc(NCOL, false, false);
             mbar_wait(w_bar, 0);
+            if (PAIR) mbar_wait(&peer_full[0], 0);     // the peer's weight slice is resident too
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
             uint32_t pr_phase[2] = {0, 0};
@@ -233,7 +246,6 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 const uint32_t d_buf = tmem_base + (uint32_t)((t & 1) * BUF_COLS);
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
-                    if (PAIR) mbar_wait(&peer_full[stage], phase);
                     if (kc == 0) FSMG_TR(t, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
@@ -467,6 +479,12 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 fence_proxy_async_all();
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (PAIR) {
+                        if (prank == 0) mbar_expect_tx(&full_bar[stage], 2 * box_bytes);
+                        tma_load_3d_2sm(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(&full_bar[stage], box_bytes);
                     if (CLS == 1) tma_load_3d(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
                     else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage], CMASK);
@@ -477,25 +495,17 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         }
     } else if (warp == 1) {
         if (lane == 0 && PAIR && prank == 1) {
-            // peer CTA: no MMA issue; relay "my half of the rows has landed" to the leader, stage by stage.  Its resident weight
-            // slice (half of B) must be complete before the first relay: wait for it here.
             mbar_wait(w_bar, 0);
-            int stage = 0; uint32_t phase = 0;
-            for (int s = 1; s < p.T; ++s)
-                for (int kc = 0; kc < KC; ++kc) {
-                    mbar_wait(&full_bar[stage], phase);
-                    mbar_arrive_remote(&peer_full[stage], 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                }
+            mbar_arrive_remote(&peer_full[0], 0);
         } else if (lane == 0) {
             constexpr uint32_t idesc = PAIR ? make_idesc_m(256, 2 * NCOL) : make_idesc(NCOL, false, false);
             mbar_wait(w_bar, 0);
+            if (PAIR) mbar_wait(&peer_full[0], 0);
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
             for (int s = 1; s < p.T; ++s) {
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&full_bar[stage], phase);
-                    if (PAIR) mbar_wait(&peer_full[stage], phase);
                     if (kc == 0) FSMG_TR(s, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
