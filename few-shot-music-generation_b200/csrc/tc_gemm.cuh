@@ -860,7 +860,7 @@ static inline int tc_init(TcContext& c) {
     const char* envs = getenv("FSMG_STREAMK");
     c.streamk = envs ? atoi(envs) : 1;
     const char* envp = getenv("FSMG_LSTM_PAIR");
-    c.lstm_pair = envp ? atoi(envp) : 0;
+    c.lstm_pair = envp ? atoi(envp) : 1;   // bit 0: backward (measured 2.64 -> 1.99 ms), bit 1: forward (neutral)
     const char* envl = getenv("FSMG_LSTM_CLUSTER");
     c.lstm_cluster = envl ? atoi(envl) : 1;
     int dev = 0;
