@@ -320,10 +320,17 @@ def main():
     lse_flops = 2.0 * tok_gpu * h_ * v1_
     achieved = lse_flops / (lse_ms * 1e-3) / 1e12 if lse_ms > 0 else 0.0
     step_tflops = f_tok * tok_gpu / (ms_step * 1e-3) / 1e12
+    traffic = None
+    tf = ROOT / "profiles" / "r1_traffic.json"
+    if tf.exists():   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+        try:
+            traffic = float(json.loads(tf.read_text())["dram_bytes_per_launch"])
+        except Exception:
+            traffic = None
     roofline = dict(bound="tensor", kernel="tc::tc_gemm_kernel<256, EPI_LSE> projection logits + online log-sum-exp "
                     f"({n_launch} launches/step, {lse_flops / n_launch / 1e9:.2f} GFLOP each)",
                     achieved=achieved, peak=pk["tflops_burst"], unit="TFLOP/s", frac=achieved / pk["tflops_burst"],
-                    traffic=None, peak_source=pk["source"] + " burst bf16 (kernel timed alone between events)",
+                    traffic=traffic, peak_source=pk["source"] + " burst bf16 (kernel timed alone between events)",
                     avg_launch_us=lse_ms * 1e3 / n_launch,
                     whole_step=dict(achieved=step_tflops, peak=pk["tflops"], frac=step_tflops / pk["tflops"],
                                     note="algorithmic 3*(2(E+H)4H+2HV') FLOP/token over the full optimizer step vs sustained bf16 peak"))

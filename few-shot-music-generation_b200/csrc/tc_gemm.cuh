@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restr
 #pragma unroll
     for (int e = 0; e < 8; ++e) csum[e] = 0.0f;
     __half* base = logits + (int64_t)r_begin * ld + v0;
+    const bool interior = v0 + 8 <= vp1;
     constexpr int RB = 8;
     for (int lr0 = 0; lr0 < n_rows; lr0 += RB) {
         uint4 raw[RB];
@@ -794,18 +795,30 @@ __global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restr
 #pragma unroll
         for (int b = 0; b < RB; ++b) {
             if (lr0 + b < n_rows) {
-                const float lse = s_lse[lr0 + b];
+                const float nl2 = -s_lse[lr0 + b] * 1.4426950408889634f;      // exp(x - lse) = ex2(x*log2e - lse*log2e): one FFMA + MUFU
                 const int tg = s_tgt[lr0 + b] - v0;
                 __half2* h2 = reinterpret_cast<__half2*>(&raw[b]);
+                if (interior && (unsigned)tg >= 8u) {      // fast path: no column guards, no target in these 8 columns
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float2 f = __half22float2(h2[q]);
-                    const int v = v0 + 2 * q;
-                    const float a = v < vp1 ? __expf(f.x - lse) - (2 * q == tg ? 1.0f : 0.0f) : 0.0f;
-                    const float bb = v + 1 < vp1 ? __expf(f.y - lse) - (2 * q + 1 == tg ? 1.0f : 0.0f) : 0.0f;
-                    h2[q] = __floats2half2_rn(a, bb);
-                    csum[2 * q] += a;
-                    csum[2 * q + 1] += bb;
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(h2[q]);
+                        const float a = exp2f(fmaf(f.x, 1.4426950408889634f, nl2));
+                        const float bb = exp2f(fmaf(f.y, 1.4426950408889634f, nl2));
+                        h2[q] = __floats2half2_rn(a, bb);
+                        csum[2 * q] += a;
+                        csum[2 * q + 1] += bb;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(h2[q]);
+                        const int v = v0 + 2 * q;
+                        const float a = v < vp1 ? exp2f(fmaf(f.x, 1.4426950408889634f, nl2)) - (2 * q == tg ? 1.0f : 0.0f) : 0.0f;
+                        const float bb = v + 1 < vp1 ? exp2f(fmaf(f.y, 1.4426950408889634f, nl2)) - (2 * q + 1 == tg ? 1.0f : 0.0f) : 0.0f;
+                        h2[q] = __floats2half2_rn(a, bb);
+                        csum[2 * q] += a;
+                        csum[2 * q + 1] += bb;
+                    }
                 }
                 *reinterpret_cast<uint4*>(base + (int64_t)(lr0 + b) * ld) = raw[b];
             }
@@ -1084,7 +1097,7 @@ static inline int tc_projection_post(TcContext& c, int n_part, const int32_t* y,
     if (!logits16) {
         tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
     } else {
-        constexpr int ROWS = 128;   // rows per strip: one atomicAdd per column per 128 rows for the bias gradient
+        constexpr int ROWS = 32;    // rows per strip (measured: 32 -> 1.87 ms, 128 -> 2.45 ms per step: more, smaller CTAs stream better)
         tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
         dim3 grid(cdiv(ld16, 1024), cdiv(mc, ROWS));
         tc::softmax_grad_strip_kernel<ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
