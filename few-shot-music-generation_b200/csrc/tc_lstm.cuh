@@ -367,10 +367,10 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     for (int e = 0; e < 8; ++e) {
                         // 5 ex2 + 3 rcp per unit instead of 5 + 5 (the epilogue is MUFU-bound): sigmoid(a) and tanh(b) share one
                         // reciprocal of (1+e^-a)(1+e^-2b).  Exponents are clamped at 2^57 so the product cannot overflow.
-                        const float ea = exp2f(fminf(-1.4426950408889634f * acc[0][e], 57.0f));
-                        const float eb = exp2f(fminf(-2.8853900817779268f * acc[1][e], 57.0f));
-                        const float ef = exp2f(fminf(-1.4426950408889634f * (acc[2][e] + 1.0f), 57.0f));   // forget_bias = 1 (A.2)
-                        const float eo = exp2f(fminf(-1.4426950408889634f * acc[3][e], 57.0f));
+                        const float ea = fast_ex2(fminf(-1.4426950408889634f * acc[0][e], 57.0f));
+                        const float eb = fast_ex2(fminf(-2.8853900817779268f * acc[1][e], 57.0f));
+                        const float ef = fast_ex2(fminf(-1.4426950408889634f * (acc[2][e] + 1.0f), 57.0f));   // forget_bias = 1 (A.2)
+                        const float eo = fast_ex2(fminf(-1.4426950408889634f * acc[3][e], 57.0f));
                         const float r1 = __fdividef(1.0f, (1.0f + ea) * (1.0f + eb));
                         const float i_ = r1 * (1.0f + eb);
                         const float j_ = (1.0f - eb) * (r1 * (1.0f + ea));
@@ -378,7 +378,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                         const float cv = c_state[u0 + e] * f_ + i_ * j_;
                         c_state[u0 + e] = cv;
                         cn[e] = cv;
-                        const float ec = exp2f(fminf(-2.8853900817779268f * cv, 57.0f));
+                        const float ec = fast_ex2(fminf(-2.8853900817779268f * cv, 57.0f));
                         const float r2 = __fdividef(1.0f, (1.0f + ec) * (1.0f + eo));
                         const float o_ = r2 * (1.0f + ec);
                         const float tc_ = (1.0f - ec) * (r2 * (1.0f + eo));
