@@ -23,9 +23,9 @@ namespace tc {
 constexpr int BM = 128;      // UMMA M (cta_group::1)
 constexpr int BK = 64;       // 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;                 // two epilogue warpgroups: each owns half of the tile's columns
+constexpr int NUM_EPI_WARPS = 16;                // four epilogue warpgroups (4 warps per SM sub-partition): each owns a quarter of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
-constexpr int EPI_STAGE_BYTES = 4096;            // per epilogue warp: 32 rows x 32 fp32 staging (swizzled)
+constexpr int EPI_STAGE_BYTES = 2048;            // per epilogue warp: 32 rows x 16 fp32 staging (swizzled) / 1 KB fp16 staging + bias
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -165,6 +165,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait for outstanding tcgen05.ld and tie the destination registers to the wait, so that no use of them can be
@@ -387,11 +402,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue warps 2..9: TMEM lane quadrant = warp % 4; warpgroup (warp-2)/4 owns half of the columns =====
+        // ===== epilogue warps 2..17: TMEM lane quadrant = warp % 4; warpgroup (warp-2)/4 owns a quarter of the tile's columns,
+        // processed in 16-column chunks (registers: 576 threads have to fit, and 4 warps per sub-partition hide each other's latencies)
         const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;
-        constexpr int CHUNKS = BN / 64;                        // 32-column chunks per warp
-        float4* st4 = reinterpret_cast<float4*>(epi_smem + (warp - 2) * EPI_STAGE_BYTES);
+        const int cg = (warp - 2) >> 2;                          // column group 0..3
+        constexpr int CW = 16;
+        constexpr int GCOLS = BN / 4;                            // columns per warp
+        constexpr int CHUNKS = GCOLS / CW;                       // 4 (BN = 256) or 2 (BN = 128)
+        uint8_t* stg = epi_smem + (warp - 2) * EPI_STAGE_BYTES;
+        float4* st4 = reinterpret_cast<float4*>(stg);            // fp32 staging: 32 rows x 4 float4, slot c4 ^ ((row >> 1) & 3)
+        uint4* sh4 = reinterpret_cast<uint4*>(stg);              // fp16 staging: 32 rows x 2 uint4, slot c2 ^ ((row >> 2) & 1)
+        float* bias_s = reinterpret_cast<float*>(stg + 1024);    // EPI_LSE: bias of this warp's GCOLS columns
         int acc = 0; uint32_t acc_phase = 0;
         WorkIter it(sh, cluster_id, n_clusters);
         int tile_mn, kb0, kb1;
@@ -400,28 +421,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int row_w0 = m_blk * BM + quad * 32;            // first row of this warp
             const int row = row_w0 + lane;                         // row held by this thread in TMEM
             const bool row_ok = row < sh.M;
-            const uint32_t t_row = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+            const int cb = n_blk * BN + cg * GCOLS;                // first column of this warp
+            const uint32_t t_row = tmem_base + acc * BN + cg * GCOLS + ((uint32_t)(quad * 32) << 16);
             float run_max = -INFINITY, run_sum = 0.0f;
             float sq_acc = 0.0f;
             int tgt_col = -1;
-            if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - n_blk * BN;
-            // bias of every chunk of this tile, fetched before the accumulator is awaited (off the critical path)
-            // EPI_LSE: the bias of this warp's columns goes to smem once per tile (read back as broadcast float4s)
-            float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(st4) + 2048);
-            if (EPI == EPI_LSE) {
+            if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - cb;
+            if (EPI == EPI_LSE) {     // bias of this warp's columns -> smem once per tile (read back as broadcast float4s)
 #pragma unroll
-                for (int cc = 0; cc < CHUNKS; ++cc) {
-                    const int colb = n_blk * BN + (half * CHUNKS + cc) * 32 + lane;
-                    bias_s[cc * 32 + lane] = colb < sh.N ? ep.bias[colb] : 0.0f;
+                for (int i = 0; i < GCOLS / 32; ++i) {
+                    const int colb = cb + i * 32 + lane;
+                    bias_s[i * 32 + lane] = colb < sh.N ? ep.bias[colb] : 0.0f;
                 }
                 __syncwarp();
             }
             float4 bias4[CHUNKS];
-            if (EPI == EPI_STORE) {
+            if (EPI == EPI_STORE) {   // bias of the 4 columns this lane writes out, fetched before the accumulator is awaited
                 const bool add_bias = ep.bias != nullptr && kb0 == 0;   // the piece that starts the K range carries the bias
 #pragma unroll
                 for (int cc = 0; cc < CHUNKS; ++cc) {
-                    const int colv = n_blk * BN + (half * CHUNKS + cc) * 32 + 4 * (lane & 7);
+                    const int colv = cb + cc * CW + 4 * (lane & 3);
                     bias4[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (add_bias) {
                         if (colv + 3 < sh.N) bias4[cc] = *reinterpret_cast<const float4*>(ep.bias + colv);   // bias tensors are 256-B aligned
@@ -434,187 +453,175 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            uint32_t rbuf[2][32];
-            tmem_ld32(t_row + (half * CHUNKS) * 32, rbuf[0]);
+            uint32_t rbuf[2][16];
+            tmem_ld16(t_row, rbuf[0]);
 #pragma unroll
             for (int cc = 0; cc < CHUNKS; ++cc) {
-                const int c = half * CHUNKS + cc;
-                uint32_t (&r)[32] = rbuf[cc & 1];
-                tmem_ld_wait_dep(r);
-                if (cc + 1 < CHUNKS) tmem_ld32(t_row + (c + 1) * 32, rbuf[(cc + 1) & 1]);   // next chunk streams in while this one is processed
-                const int col0 = n_blk * BN + c * 32;
+                uint32_t (&r)[16] = rbuf[cc & 1];
+                tmem_ld_wait_dep16(r);
+                if (cc + 1 < CHUNKS) tmem_ld16(t_row + (cc + 1) * CW, rbuf[(cc + 1) & 1]);   // next chunk streams in meanwhile
+                const int col0 = cb + cc * CW;
                 if (col0 >= sh.N) continue;   // warp-uniform
-                const bool full = col0 + 32 <= sh.N;
-                if (EPI == EPI_STORE) {
-                    // phase 1: registers (one row per lane) -> swizzled smem (16-byte slot c8 ^ (row & 7))
+                const bool full = col0 + CW <= sh.N;
+                if (EPI == EPI_STORE || EPI == EPI_SCATTER) {
+                    // phase 1: registers (one row per lane) -> swizzled smem
 #pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8)
-                        st4[lane * 8 + (c8 ^ (lane & 7))] =
-                            make_float4(ep.alpha * __uint_as_float(r[4 * c8]), ep.alpha * __uint_as_float(r[4 * c8 + 1]),
-                                        ep.alpha * __uint_as_float(r[4 * c8 + 2]), ep.alpha * __uint_as_float(r[4 * c8 + 3]));
+                    for (int c4 = 0; c4 < 4; ++c4)
+                        st4[lane * 4 + (c4 ^ ((lane >> 1) & 3))] =
+                            make_float4(ep.alpha * __uint_as_float(r[4 * c4]), ep.alpha * __uint_as_float(r[4 * c4 + 1]),
+                                        ep.alpha * __uint_as_float(r[4 * c4 + 2]), ep.alpha * __uint_as_float(r[4 * c4 + 3]));
                     __syncwarp();
-                    // phase 2: 8 lanes cover one 128-byte row segment, 4 rows per instruction -> coalesced lines
-                    const int c8 = lane & 7;
-                    const int colv = col0 + 4 * c8;
-                    const float4 b4 = bias4[cc];
+                    // phase 2: 4 lanes cover one 64-byte row segment, 8 rows per instruction -> coalesced sectors
+                    const int c4 = lane & 3;
+                    const int colv = col0 + 4 * c4;
                     const bool vec = full && ep.vec_ok;
-                    float4 v[8];
+                    float4 v[4];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int rr = 4 * k + (lane >> 3);
-                        v[k] = st4[rr * 8 + (c8 ^ (rr & 7))];
-                        v[k].x += b4.x; v[k].y += b4.y; v[k].z += b4.z; v[k].w += b4.w;
+                    for (int k = 0; k < 4; ++k) {
+                        const int rr = 8 * k + (lane >> 2);
+                        v[k] = st4[rr * 4 + (c4 ^ ((rr >> 1) & 3))];
                     }
-                    if (ep.c_half) {
-                        __half* C = reinterpret_cast<__half*>(ep.C);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int grow = row_w0 + 4 * k + (lane >> 3);
-                            if (grow >= sh.M) continue;
-                            __half* dst = C + (int64_t)grow * ep.ldc + colv;
-                            if (vec) {
-                                __align__(8) __half2 hh[2] = {__floats2half2_rn(v[k].x, v[k].y), __floats2half2_rn(v[k].z, v[k].w)};
-                                *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hh);
-                            } else {
-                                if (colv < sh.N) dst[0] = __float2half_rn(v[k].x);
-                                if (colv + 1 < sh.N) dst[1] = __float2half_rn(v[k].y);
-                                if (colv + 2 < sh.N) dst[2] = __float2half_rn(v[k].z);
-                                if (colv + 3 < sh.N) dst[3] = __float2half_rn(v[k].w);
-                            }
-                        }
-                    } else {
+                    if (EPI == EPI_SCATTER) {
                         float* C = reinterpret_cast<float*>(ep.C);
-                        if (vec && ep.accumulate && !ep.atomic) {
-                            float4 o[8];   // all (coalesced) loads in flight before the first dependent add/store
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int grow = row_w0 + 4 * k + (lane >> 3);
-                                o[k] = grow < sh.M ? __ldcg(reinterpret_cast<const float4*>(C + (int64_t)grow * ep.ldc + colv)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                            }
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) { v[k].x += o[k].x; v[k].y += o[k].y; v[k].z += o[k].z; v[k].w += o[k].w; }
-                        }
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const int grow = row_w0 + 4 * k + (lane >> 3);
+                        for (int k = 0; k < 4; ++k) {
+                            const int grow = row_w0 + 8 * k + (lane >> 2);
                             if (grow >= sh.M) continue;
-                            float* dst = C + (int64_t)grow * ep.ldc + colv;
+                            float* dst = C + (int64_t)ep.y[ep.row0 + grow] * ep.ldc + colv;
                             if (vec) {
-                                if (ep.atomic)
-                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
-                                else
-                                    *reinterpret_cast<float4*>(dst) = v[k];
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
+                                sq_acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
                             } else {
                                 const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    if (colv + e < sh.N) {
-                                        if (ep.atomic) atomicAdd(dst + e, e4[e]);
-                                        else if (ep.accumulate) dst[e] += e4[e];
-                                        else dst[e] = e4[e];
+                                for (int e = 0; e < 4; ++e)
+                                    if (colv + e < sh.N) { atomicAdd(dst + e, e4[e]); sq_acc += e4[e] * e4[e]; }
+                            }
+                        }
+                    } else {
+                        const float4 b4 = bias4[cc];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { v[k].x += b4.x; v[k].y += b4.y; v[k].z += b4.z; v[k].w += b4.w; }
+                        if (ep.c_half) {
+                            __half* C = reinterpret_cast<__half*>(ep.C);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int grow = row_w0 + 8 * k + (lane >> 2);
+                                if (grow >= sh.M) continue;
+                                __half* dst = C + (int64_t)grow * ep.ldc + colv;
+                                if (vec) {
+                                    __align__(8) __half2 hh[2] = {__floats2half2_rn(v[k].x, v[k].y), __floats2half2_rn(v[k].z, v[k].w)};
+                                    *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(hh);
+                                } else {
+                                    if (colv < sh.N) dst[0] = __float2half_rn(v[k].x);
+                                    if (colv + 1 < sh.N) dst[1] = __float2half_rn(v[k].y);
+                                    if (colv + 2 < sh.N) dst[2] = __float2half_rn(v[k].z);
+                                    if (colv + 3 < sh.N) dst[3] = __float2half_rn(v[k].w);
+                                }
+                            }
+                        } else {
+                            float* C = reinterpret_cast<float*>(ep.C);
+                            if (vec && ep.accumulate && !ep.atomic) {
+                                float4 o[4];   // all (coalesced) loads in flight before the first dependent add/store
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const int grow = row_w0 + 8 * k + (lane >> 2);
+                                    o[k] = grow < sh.M ? __ldcg(reinterpret_cast<const float4*>(C + (int64_t)grow * ep.ldc + colv)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) { v[k].x += o[k].x; v[k].y += o[k].y; v[k].z += o[k].z; v[k].w += o[k].w; }
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int grow = row_w0 + 8 * k + (lane >> 2);
+                                if (grow >= sh.M) continue;
+                                float* dst = C + (int64_t)grow * ep.ldc + colv;
+                                if (vec) {
+                                    if (ep.atomic)
+                                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
+                                    else
+                                        *reinterpret_cast<float4*>(dst) = v[k];
+                                } else {
+                                    const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        if (colv + e < sh.N) {
+                                            if (ep.atomic) atomicAdd(dst + e, e4[e]);
+                                            else if (ep.accumulate) dst[e] += e4[e];
+                                            else dst[e] = e4[e];
+                                        }
                                     }
                                 }
                             }
                         }
                     }
                     __syncwarp();   // staging buffer is reused by the next chunk
-                } else if (EPI == EPI_SCATTER) {
-#pragma unroll
-                    for (int c8 = 0; c8 < 8; ++c8)
-                        st4[lane * 8 + (c8 ^ (lane & 7))] =
-                            make_float4(ep.alpha * __uint_as_float(r[4 * c8]), ep.alpha * __uint_as_float(r[4 * c8 + 1]),
-                                        ep.alpha * __uint_as_float(r[4 * c8 + 2]), ep.alpha * __uint_as_float(r[4 * c8 + 3]));
-                    __syncwarp();
-                    const int c8 = lane & 7;
-                    const int colv = col0 + 4 * c8;
-                    const bool vec = full && ep.vec_ok;
-                    float* C = reinterpret_cast<float*>(ep.C);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int rr = 4 * k + (lane >> 3);
-                        const int grow = row_w0 + rr;
-                        if (grow >= sh.M) continue;
-                        const float4 v = st4[rr * 8 + (c8 ^ (rr & 7))];
-                        float* dst = C + (int64_t)ep.y[ep.row0 + grow] * ep.ldc + colv;
-                        if (vec) {
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-                            sq_acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-                        } else {
-                            const float e4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (colv + e < sh.N) { atomicAdd(dst + e, e4[e]); sq_acc += e4[e] * e4[e]; }
-                        }
-                    }
-                    __syncwarp();
                 } else {  // EPI_LSE
-                    // bias for this chunk: one coalesced load, then broadcast by shuffle
-                    float v[32];
+                    float v[CW];
                     float cmax = -INFINITY;
-                    float cm4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                     if (full) {   // warp-uniform fast path: no per-element column guards
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
+                        for (int j = 0; j < CW; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * CW + j);
                             v[j] = __uint_as_float(r[j]) + b4.x;
                             v[j + 1] = __uint_as_float(r[j + 1]) + b4.y;
                             v[j + 2] = __uint_as_float(r[j + 2]) + b4.z;
                             v[j + 3] = __uint_as_float(r[j + 3]) + b4.w;
-                            cm4[(j >> 2) & 3] = fmaxf(cm4[(j >> 2) & 3], fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
                         }
-                        cmax = fmaxf(fmaxf(cm4[0], cm4[1]), fmaxf(cm4[2], cm4[3]));
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + j);
+                        for (int j = 0; j < CW; j += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * CW + j);
                             v[j] = (col0 + j < sh.N) ? __uint_as_float(r[j]) + b4.x : -INFINITY;
                             v[j + 1] = (col0 + j + 1 < sh.N) ? __uint_as_float(r[j + 1]) + b4.y : -INFINITY;
                             v[j + 2] = (col0 + j + 2 < sh.N) ? __uint_as_float(r[j + 2]) + b4.z : -INFINITY;
                             v[j + 3] = (col0 + j + 3 < sh.N) ? __uint_as_float(r[j + 3]) + b4.w : -INFINITY;
-                            cmax = fmaxf(cmax, fmaxf(fmaxf(v[j], v[j + 1]), fmaxf(v[j + 2], v[j + 3])));
                         }
                     }
-                    const int tj = tgt_col - c * 32;
-                    if (row_ok && tj >= 0 && tj < 32) {
+                    {
+                        const float m0 = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), m1 = fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7]));
+                        const float m2 = fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11])), m3 = fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]));
+                        cmax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                    }
+                    const int tj = tgt_col - cc * CW;
+                    if (row_ok && tj >= 0 && tj < CW) {
                         float tv = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) tv = (j == tj) ? v[j] : tv;
+                        for (int j = 0; j < CW; ++j) tv = (j == tj) ? v[j] : tv;
                         ep.tgt[row] = tv;
                     }
                     const float nmax = fmaxf(run_max, cmax);
                     const float nmax_l2 = nmax * 1.4426950408889634f;
-                    float sa0 = 0.0f, sa1 = 0.0f, sa2 = 0.0f, sa3 = 0.0f;   // four independent chains: the 32-long serial FADD chain was latency-bound
+                    float sa0 = 0.0f, sa1 = 0.0f, sa2 = 0.0f, sa3 = 0.0f;   // independent chains
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < CW; j += 4) {
                         sa0 += fast_ex2(fmaf(v[j], 1.4426950408889634f, -nmax_l2));          // one FFMA + MUFU.EX2 per logit
                         sa1 += fast_ex2(fmaf(v[j + 1], 1.4426950408889634f, -nmax_l2));
                         sa2 += fast_ex2(fmaf(v[j + 2], 1.4426950408889634f, -nmax_l2));
                         sa3 += fast_ex2(fmaf(v[j + 3], 1.4426950408889634f, -nmax_l2));
                     }
-                    const float sacc = (sa0 + sa1) + (sa2 + sa3);
-                    run_sum = run_sum * __expf(run_max - nmax) + sacc;
+                    run_sum = run_sum * __expf(run_max - nmax) + ((sa0 + sa1) + (sa2 + sa3));
                     run_max = nmax;
                     if (ep.logits16) {
-                        // fp16 logits for the backward: staged through smem (64-B rows, slot c ^ ((row>>1)&3)) -> coalesced stores
-                        uint4* sh4 = reinterpret_cast<uint4*>(st4);
+                        // fp16 logits for the backward: staged through smem (32-B rows) -> 16 rows x 32 B per store instruction
 #pragma unroll
-                        for (int c4 = 0; c4 < 4; ++c4) {
+                        for (int c2 = 0; c2 < 2; ++c2) {
                             __align__(16) __half2 hh[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) hh[q] = __floats2half2_rn(v[8 * c4 + 2 * q], v[8 * c4 + 2 * q + 1]);
-                            sh4[lane * 4 + (c4 ^ ((lane >> 1) & 3))] = *reinterpret_cast<uint4*>(hh);
+                            for (int q = 0; q < 4; ++q) hh[q] = __floats2half2_rn(v[8 * c2 + 2 * q], v[8 * c2 + 2 * q + 1]);
+                            sh4[lane * 2 + (c2 ^ ((lane >> 2) & 1))] = *reinterpret_cast<uint4*>(hh);
                         }
                         __syncwarp();
-                        const int c4 = lane & 3;
-                        const int colh = col0 + 8 * c4;
+                        const int c2 = lane & 1;
+                        const int colh = col0 + 8 * c2;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const int rr = 8 * k + (lane >> 2);
+                        for (int k = 0; k < 2; ++k) {
+                            const int rr = 16 * k + (lane >> 1);
                             const int grow = row_w0 + rr;
-                            uint4 pk = sh4[rr * 4 + (c4 ^ ((rr >> 1) & 3))];
+                            uint4 pk = sh4[rr * 2 + (c2 ^ ((rr >> 2) & 1))];
                             if (grow < sh.M) {
                                 __half* dst = ep.logits16 + (int64_t)grow * ep.ld16 + colh;
-                                if (colh + 8 <= sh.N) *reinterpret_cast<uint4*>(dst) = pk;   // ld16 % 8 == 0, col0 % 32 == 0 -> 16-B aligned
+                                if (colh + 8 <= sh.N) *reinterpret_cast<uint4*>(dst) = pk;   // ld16 % 8 == 0, col0 % 16 == 0 -> 16-B aligned
                                 else {
                                     const __half* ph = reinterpret_cast<const __half*>(&pk);
 #pragma unroll
@@ -627,7 +634,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
-            if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk * 2 + half] = make_float2(run_max, run_sum);
+            if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk * 4 + cg] = make_float2(run_max, run_sum);
             if (EPI == EPI_SCATTER) {
                 sq_acc = warp_sum(sq_acc);
                 if (lane == 0 && sq_acc != 0.0f) atomicAdd(ep.tgt, sq_acc);
@@ -865,7 +872,7 @@ struct TcContext {
 
 template <typename B>
 static inline void tc_carve(TcContext& c, B& b, int /*Nmax*/, int /*T*/, int V1, int /*Vp*/, int /*H*/, int chunk_rows) {
-    c.part_tiles = 2 * cdiv(V1, 128);   // two column halves per N tile
+    c.part_tiles = 4 * cdiv(V1, 128);   // four column groups per N tile
     c.part = b.template take<float2>((int64_t)chunk_rows * c.part_tiles);
     c.tgt = b.template take<float>(chunk_rows);
     c.counters = b.template take<int>(256);
@@ -1089,9 +1096,9 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     TcPlan p = tc_plan(c, mc, V1, H, false);
     tc::EpiParams ep;
     memset(&ep, 0, sizeof ep);
-    ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 2 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
+    ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 4 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
     ep.logits16 = logits16; ep.ld16 = ld16;
-    *n_part_out = 2 * p.sh.n_n;
+    *n_part_out = 4 * p.sh.n_n;
     CUtensorMap ma, mb;
     int rc = tc_make_maps(c, g, false, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;
