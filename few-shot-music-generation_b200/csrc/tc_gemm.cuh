@@ -77,6 +77,17 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
         "l"(map), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
         : "memory");
 }
+// cta_group::2 flavour: data lands in THIS CTA's smem, the complete_tx goes to the mbarrier at the same offset in CTA 0 of the pair
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar_local) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 rb;\n"
+        "mapa.shared::cluster.u32 rb, %2, 0;\n"
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [rb];\n"
+        "}\n" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar_local)), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -211,6 +222,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_m(int m, int n) {   // K-major operands, explicit M (256 for cta_group::2)
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc_full(int m, int n, bool a_mn, bool b_mn) {
+    return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
     return (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -278,24 +292,25 @@ struct WorkIter {
     }
 };
 
-template <int BN>
+template <int BN, int CL>
 struct SmemLayout {
-    static constexpr int A_BYTES = BM * BK * 2;        // 16 KB
-    static constexpr int B_BYTES = BN * BK * 2;        // 32 KB (BN=256) / 16 KB (BN=128)
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int A_BYTES = BM * BK * 2;              // 16 KB
+    static constexpr int B_BYTES = (BN / CL) * BK * 2;       // CL = 2 (cta_group::2): each CTA of the pair holds half of the B tile
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 / 32 / 24 KB
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
     static constexpr int BAR_BYTES = 256;
     static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-// CL = 2: thread-block cluster of two CTAs working on two vertically adjacent output tiles (same N tile).  Each CTA
-// fetches HALF of the shared B tile and TMA-multicasts it to both, cutting the L2->SMEM operand traffic by a third
-// (the K-streaming mainloop of a 128 x 256 tile is L2-bandwidth bound: 96 B/clk/SM at full tensor rate).
+// CL = 2: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 of 256 x BN x 16 per K step: each CTA streams its own 128
+// rows of A and only HALF of the B tile, the tensor cores read both CTAs' shared memory.  The K-streaming mainloop is bound by the
+// bytes that must LAND in each SM's smem (measured ~40 B/clk/SM; a 1-SM 128 x 256 tile needs 96 B/clk at full tensor rate) —
+// TMA multicast (the previous CL = 2 scheme) cut L2 reads but not that ingest; the 2-SM MMA cuts it by a third.
 template <int BN, int EPI, bool A_MN, bool B_MN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape sh, EpiParams ep) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, CL>;
     constexpr int STAGES = L::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // keep the pointer in the shared address space (pointer arithmetic on the extern array, no integer round trip):
@@ -316,11 +331,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a);
         tma_prefetch_desc(&map_b);
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], NUM_EPI_WARPS); }
+        // CL = 2 (cta_group::2): the leader's full barrier collects both CTAs' TMA bytes, its tmem_empty both CTAs' epilogue warps;
+        // empty / tmem_full are signalled in both CTAs by the leader's multicast tcgen05.commit
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CL * NUM_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_base_slot, 2 * BN);   // 2 accumulator stages of BN fp32 columns
+    if (warp == 1) { if (CL == 2) tmem_alloc_2sm(tmem_base_slot, 2 * BN); else tmem_alloc(tmem_base_slot, 2 * BN); }   // 2 accumulator stages
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();      // peer barriers are initialised before any multicast / remote arrive
@@ -339,29 +356,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
-                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                    if (A_MN) {
-#pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &full_bar[stage]);
-                    } else {
-                        tma_load_2d(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
-                    }
                     if (CL == 1) {
+                        mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                        if (A_MN) {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &full_bar[stage]);
+                        } else {
+                            tma_load_2d(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                        }
                         if (B_MN) {
 #pragma unroll
                             for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &map_b, n_blk * BN + j * 64, kb * BK, &full_bar[stage]);
                         } else {
                             tma_load_2d(sb, &map_b, kb * BK, n_blk * BN, &full_bar[stage]);
                         }
-                    } else {   // this CTA fetches its half of the B tile and multicasts it to both CTAs of the cluster
+                    } else {
+                        // cta_group::2: this CTA streams ITS 128 rows of A and ITS half of the B tile (the tensor core reads both CTAs'
+                        // smem); every load completes on the leader's barrier, which therefore expects both CTAs' bytes
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        if (A_MN) {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &full_bar[stage]);
+                        } else {
+                            tma_load_2d_2sm(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                        }
                         if (B_MN) {
 #pragma unroll
-                            for (int jj = 0; jj < BN / 128; ++jj) {
-                                const int j = cta_rank * (BN / 128) + jj;
-                                tma_load_2d_mc(sb + j * 8192, &map_b, n_blk * BN + j * 64, kb * BK, &full_bar[stage], (uint16_t)0x3);
-                            }
+                            for (int jj = 0; jj < BN / 128; ++jj)
+                                tma_load_2d_2sm(sb + jj * 8192, &map_b, n_blk * BN + (cta_rank * (BN / 128) + jj) * 64, kb * BK, &full_bar[stage]);
                         } else {
-                            tma_load_2d_mc(sb + cta_rank * (BN / 2) * 128, &map_b, kb * BK, n_blk * BN + cta_rank * (BN / 2), &full_bar[stage], (uint16_t)0x3);
+                            tma_load_2d_2sm(sb, &map_b, kb * BK, n_blk * BN + cta_rank * (BN / 2), &full_bar[stage]);
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -369,9 +393,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+        // ===== MMA issuer (one thread; with cta_group::2 only the leader CTA of the pair issues, for both) =====
+        if (lane == 0 && cta_rank == 0) {
+            constexpr uint32_t idesc = (CL == 2) ? make_idesc_full(256, BN, A_MN, B_MN) : make_idesc(BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             WorkIter it(sh, cluster_id, n_clusters);
@@ -391,13 +415,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // MN-major SW128: atom = 8 k-rows x 64 mn, SBO = 1024 B (next 8 k), LBO = 8192 B (next 64 mn), +2048 B per UMMA_K.
                         const uint64_t a_desc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
                         const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-                        umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (CL == 2) umma_f16_2sm(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // 256 x BN x 16 over both SMs
+                        else umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    if (CL == 2) umma_commit_mc(&empty_bar[stage], (uint16_t)0x3);   // both CTAs' producers write into both CTAs' stage
+                    if (CL == 2) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);   // frees the stage in both CTAs
                     else umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+                if (CL == 2) umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);   // accumulators complete in both CTAs -> both epilogues
+                else umma_commit(&tmem_full[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -641,14 +667,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);   // NUM_EPI_WARPS arrivals free the accumulator stage
+            if (lane == 0) {   // all epilogue warps (of both CTAs when paired) free the accumulator stage for the leader's MMA thread
+                if (CL == 2 && cta_rank == 1) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (CL == 2) cluster_sync_all();      // no CTA exits while its peer may still multicast into it / signal its barriers
-    if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+    if (CL == 2) cluster_sync_all();      // no CTA exits while its peer may still read its smem / signal its barriers
+    if (warp == 1) { if (CL == 2) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN); }
 }
 
 // combine the per-(row, n-tile) (max, sumexp) partials: lse = M + log(sum_i s_i * exp(m_i - M)); nll = lse - tgt
@@ -901,9 +929,9 @@ static inline int tc_init(TcContext& c) {
     c.encode = reinterpret_cast<PFN_tensorMapEncodeTiled>(fn);
 #define FSMG_SET_SMEM(BN, EPI, AM, BMN)                                                                                  \
     FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      tc::SmemLayout<BN>::TOTAL));                                                       \
+                                      tc::SmemLayout<BN, 1>::TOTAL));                                                    \
     FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      tc::SmemLayout<BN>::TOTAL))
+                                      tc::SmemLayout<BN, 2>::TOTAL))
     FSMG_SET_SMEM(256, tc::EPI_STORE, false, false);
     FSMG_SET_SMEM(256, tc::EPI_STORE, true, true);
     FSMG_SET_SMEM(128, tc::EPI_STORE, false, false);
@@ -1016,8 +1044,8 @@ template <int EPI>
 static inline int tc_launch(const TcContext& c, const TcPlan& p, const CUtensorMap& ma, const CUtensorMap& mb, bool mn,
                             const tc::EpiParams& ep, cudaStream_t s) {
 #define FSMG_GO(BN, MN)                                                                                                   \
-    (p.cl == 2 ? tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 2>, p, tc::SmemLayout<BN>::TOTAL, ma, mb, ep, s)       \
-               : tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 1>, p, tc::SmemLayout<BN>::TOTAL, ma, mb, ep, s))
+    (p.cl == 2 ? tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 2>, p, tc::SmemLayout<BN, 2>::TOTAL, ma, mb, ep, s)       \
+               : tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 1>, p, tc::SmemLayout<BN, 1>::TOTAL, ma, mb, ep, s))
     int rc = 0;
     if constexpr (EPI == tc::EPI_LSE || EPI == tc::EPI_SCATTER) {
         rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
