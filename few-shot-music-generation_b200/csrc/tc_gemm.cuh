@@ -892,7 +892,8 @@ struct TcContext {
     int* counters = nullptr;   // [256] group-progress counters of the persistent recurrent kernels
     long long* trace = nullptr; // [128] debug timeline (FSMG_TRACE=1)
     int enabled = 1;
-    int cluster = 2;           // CTAs per cluster of the GEMM core (2 = B-tile multicast pairs, 1 = no clusters)
+    int cluster = 2;           // CTAs per cluster of the GEMM core (2 = cta_group::2 pairs, 1 = single-SM MMAs)
+    int cluster_lse = 0;       // override for the logits + log-sum-exp GEMM (0 = same as `cluster`)
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
     int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
@@ -913,6 +914,8 @@ static inline int tc_init(TcContext& c) {
     c.enabled = env ? atoi(env) : 1;
     const char* envc = getenv("FSMG_CLUSTER");
     c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
+    const char* envcl = getenv("FSMG_CLUSTER_LSE");
+    c.cluster_lse = envcl ? atoi(envcl) : 0;
     const char* envs = getenv("FSMG_STREAMK");
     c.streamk = envs ? atoi(envs) : 1;
     const char* envp = getenv("FSMG_LSTM_PAIR");
@@ -979,7 +982,7 @@ struct TcPlan {
     int cl;   // cluster size (1 or 2)
 };
 
-static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split) {
+static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split, int cl_pref = 0) {
     TcPlan p;
     p.bn = (N > 128) ? 256 : 128;
     tc::GemmShape& sh = p.sh;
@@ -987,7 +990,7 @@ static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow
     sh.n_m = cdiv(M, tc::BM);
     sh.n_n = cdiv(N, p.bn);
     sh.kb_total = cdiv(K, tc::BK);
-    p.cl = (c.cluster == 2 && sh.n_m >= 2) ? 2 : 1;     // pairs need two M tiles that share a B tile
+    p.cl = ((cl_pref ? cl_pref : c.cluster) == 2 && sh.n_m >= 2) ? 2 : 1;     // pairs need two M tiles that share a B tile
     sh.n_mp = cdiv(sh.n_m, p.cl);
     const int slots = c.num_sms / p.cl;                  // concurrently resident clusters
     int tiles = sh.n_mp * sh.n_n;                        // cluster-tiles
@@ -1121,7 +1124,7 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     memset(&g, 0, sizeof g);
     g.M = mc; g.N = V1; g.K = H; g.A = hc; g.lda = ldh; g.B = WsT16; g.ldb = ldw;
     if (!tc_operands_ok(g.A, g.lda) || !tc_operands_ok(g.B, g.ldb)) return set_error(-1, "projection operands not TMA-aligned");
-    TcPlan p = tc_plan(c, mc, V1, H, false);
+    TcPlan p = tc_plan(c, mc, V1, H, false, c.cluster_lse);
     tc::EpiParams ep;
     memset(&ep, 0, sizeof ep);
     ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 4 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
