@@ -154,8 +154,21 @@ __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncol
 __device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster
+// arrive on the mbarrier at the same smem offset in CTA `cta` of the cluster.  Default semantics (.release.cta): the
+// .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR, which makes the arriving warp drain all of its outstanding global
+// stores first (measured: 17 % of the 2-SM LSE kernel's stall samples); what the waiter consumes here is TMEM / tensor-core
+// state, ordered by tcgen05.fence::before_thread_sync / after_thread_sync around the barrier, not generic memory.
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+// cluster-scope release flavour for one-shot hand-offs of generic/async-proxy DATA to the peer (cost irrelevant there)
+__device__ __forceinline__ void mbar_arrive_remote_release(uint64_t* bar, uint32_t cta) {
     asm volatile(
         "{\n"
         ".reg .b32 ra;\n"
@@ -453,13 +466,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float sq_acc = 0.0f;
             int tgt_col = -1;
             if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - cb;
-            if (EPI == EPI_LSE) {     // bias of this warp's columns -> smem once per tile (read back as broadcast float4s)
+            float bias_r[GCOLS / 32];
+            if (EPI == EPI_LSE) {     // bias of this warp's columns: loads issued now, parked in smem after the accumulator wait below
 #pragma unroll
                 for (int i = 0; i < GCOLS / 32; ++i) {
                     const int colb = cb + i * 32 + lane;
-                    bias_s[i * 32 + lane] = colb < sh.N ? ep.bias[colb] : 0.0f;
+                    bias_r[i] = colb < sh.N ? ep.bias[colb] : 0.0f;
                 }
-                __syncwarp();
             }
             float4 bias4[CHUNKS];
             if (EPI == EPI_STORE) {   // bias of the 4 columns this lane writes out, fetched before the accumulator is awaited
@@ -481,6 +494,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_after();
             uint32_t rbuf[2][16];
             tmem_ld16(t_row, rbuf[0]);
+            if (EPI == EPI_LSE) {     // read back per chunk as broadcast float4s
+#pragma unroll
+                for (int i = 0; i < GCOLS / 32; ++i) bias_s[i * 32 + lane] = bias_r[i];
+                __syncwarp();
+            }
 #pragma unroll
             for (int cc = 0; cc < CHUNKS; ++cc) {
                 uint32_t (&r)[16] = rbuf[cc & 1];

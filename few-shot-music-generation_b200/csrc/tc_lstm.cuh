@@ -231,7 +231,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
         if (lane == 0 && PAIR && prank == 1) {
             // peer CTA: no MMA issue.  Tell the leader once that this CTA's resident weight slice (half of B) has landed.
             mbar_wait(w_bar, 0);
-            mbar_arrive_remote(&peer_full[0], 0);
+            mbar_arrive_remote_release(&peer_full[0], 0);
         } else if (lane == 0) {
             constexpr uint32_t idesc = PAIR ? make_idesc_m(256, 2 * NCOL) : make_idesc(NCOL, false, false);
             mbar_wait(w_bar, 0);
@@ -508,7 +508,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     } else if (warp == 1) {
         if (lane == 0 && PAIR && prank == 1) {
             mbar_wait(w_bar, 0);
-            mbar_arrive_remote(&peer_full[0], 0);
+            mbar_arrive_remote_release(&peer_full[0], 0);
         } else if (lane == 0) {
             constexpr uint32_t idesc = PAIR ? make_idesc_m(256, 2 * NCOL) : make_idesc(NCOL, false, false);
             mbar_wait(w_bar, 0);
