@@ -81,7 +81,7 @@ struct fsmg_handle {
     int64_t ws_bytes = 0, ws_need = 0;
     bool bound = false;
     // workspace carve-up
-    int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *samp_ids = nullptr, *samp_out = nullptr, *samp_out2 = nullptr;
+    int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *tok_graph = nullptr, *samp_ids = nullptr, *samp_out = nullptr, *samp_out2 = nullptr;
     __half *emb16 = nullptr, *Ws16 = nullptr, *WsT16 = nullptr, *xemb = nullptr, *dgates = nullptr, *dlogits = nullptr;
     __half* pre16 = nullptr;   // hoisted x*Wx+b, fp16 [NT, G4p]
     float *gbuf = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
@@ -109,6 +109,11 @@ struct fsmg_handle {
     float* h_scal = nullptr;
     int64_t h_tok_elems = 0;
     int64_t launches = 0;
+    // whole forward+backward pass captured once per (n_seqs, loss scale, nll buffer) over a fixed token buffer and replayed: ~740 kernel
+    // nodes become ONE launch, so the host cannot fall behind the device (the e2e arm synchronises on the loss every step)
+    struct StepGraph { int32_t n; uint32_t ls_bits; float* nll; cudaGraphExec_t exec; int64_t launches; int seen; int failed; };
+    std::vector<StepGraph> step_graphs;
+    int use_graph = 1;
     fsmg::TcContext tc;
 };
 
@@ -147,6 +152,7 @@ static void carve(fsmg_handle* h, char* base) {
     h->x_ids = b.take<int32_t>(NT);
     h->y_ids = b.take<int32_t>(NT);
     h->tok_stage = b.take<int32_t>(NT);
+    h->tok_graph = b.take<int32_t>(NT);
     h->emb16 = b.take<__half>((int64_t)h->V1 * h->Ep);
     h->Ws16 = b.take<__half>((int64_t)h->H * h->Vp);
     h->WsT16 = b.take<__half>((int64_t)h->V1 * h->Hp);
@@ -172,6 +178,8 @@ static void carve(fsmg_handle* h, char* base) {
     // projection chunk: rows sized so the fp16 logits chunk stays L2-resident (<= ~48 MB)
     const char* env_mb = getenv("FSMG_CHUNK_MB");
     const char* env_ov = getenv("FSMG_OVERLAP");
+    const char* env_gr = getenv("FSMG_GRAPH");
+    h->use_graph = env_gr ? atoi(env_gr) : 1;
     h->overlap = env_ov ? atoi(env_ov) : 0;   // measured: with 256 MB chunks and stream-K balanced GEMMs, overlapping streams lose (16.97 vs 14.35 ms)
     const int64_t chunk_mb = env_mb ? atoi(env_mb) : 256;   // measured optimum (sweep 32..768 MB): launch efficiency beats L2 residency
     int64_t rows = (chunk_mb << 20) / ((int64_t)h->Vp * 2);
@@ -647,6 +655,7 @@ void fsmg_destroy(fsmg_handle* h) {
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (auto ev : h->prof.pool) cudaEventDestroy(ev);
     if (h->samp_graph) cudaGraphExecDestroy(h->samp_graph);
+    for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
     for (int i = 0; i < 2; ++i) {
         if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
         if (h->ev_ready[i]) cudaEventDestroy(h->ev_ready[i]);
@@ -708,6 +717,8 @@ int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, 
             FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dws[i], cudaEventDisableTiming));
         }
     }
+    for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // graphs hold the old buffer addresses
+    h->step_graphs.clear();
     h->bound = true;
     return FSMG_OK;
 }
@@ -735,14 +746,10 @@ int fsmg_forward_nll(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, fl
     return FSMG_OK;
 }
 
-int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, float loss_scale, float* d_nll, void* stream) {
-    int rc = check_call(h, n_seqs);
-    if (rc) return rc;
-    if (!h->grads) return set_error(FSMG_ERR_STATE, "no gradient buffer bound");
-    cudaStream_t s = (cudaStream_t)stream;
+static int enqueue_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, float loss_scale, float* d_nll, cudaStream_t s) {
     h->launches = 0;
     FSMG_CUDA_OK(cudaMemsetAsync(h->grads, 0, sizeof(float) * (h->n_params + FSMG_GRAD_EXTRA), s));
-    rc = forward_lstm(h, d_tokens, n_seqs, s);
+    int rc = forward_lstm(h, d_tokens, n_seqs, s);
     if (rc) return rc;
     rc = projection(h, n_seqs, true, loss_scale, d_nll, s);
     if (rc) return rc;
@@ -751,6 +758,53 @@ int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seq
     rc = backward_lstm(h, n_seqs, loss_scale, s);
     if (rc) return rc;
     FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, float loss_scale, float* d_nll, void* stream) {
+    int rc = check_call(h, n_seqs);
+    if (rc) return rc;
+    if (!h->grads) return set_error(FSMG_ERR_STATE, "no gradient buffer bound");
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool graphable = h->use_graph && !h->prof.on && !h->overlap && h->aux[1] != nullptr && getenv("FSMG_TRACE") == nullptr;
+    if (!graphable) return enqueue_forward_backward(h, d_tokens, n_seqs, loss_scale, d_nll, s);
+    uint32_t ls_bits;
+    memcpy(&ls_bits, &loss_scale, 4);
+    fsmg_handle::StepGraph* g = nullptr;
+    for (auto& e : h->step_graphs)
+        if (e.n == n_seqs && e.ls_bits == ls_bits && e.nll == d_nll) { g = &e; break; }
+    if (!g) {
+        if (h->step_graphs.size() >= 8) {   // callers that rotate through many batch sizes: drop the oldest graph
+            if (h->step_graphs.front().exec) cudaGraphExecDestroy(h->step_graphs.front().exec);
+            h->step_graphs.erase(h->step_graphs.begin());
+        }
+        h->step_graphs.push_back({n_seqs, ls_bits, d_nll, nullptr, 0, 0, 0});
+        g = &h->step_graphs.back();
+    }
+    // first sight of a configuration: plain launches (module loading, function attributes); second: capture; then replay
+    if (g->failed || g->seen++ == 0) return enqueue_forward_backward(h, d_tokens, n_seqs, loss_scale, d_nll, s);
+    // the graph reads its tokens from a fixed internal buffer, so any caller buffer replays the same graph
+    FSMG_CUDA_OK(cudaMemcpyAsync(h->tok_graph, d_tokens, sizeof(int32_t) * (size_t)n_seqs * h->T, cudaMemcpyDeviceToDevice, s));
+    d_tokens = h->tok_graph;
+    if (!g->exec) {
+        cudaStream_t cs = h->aux[1];
+        cudaGraph_t graph = nullptr;
+        FSMG_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_forward_backward(h, d_tokens, n_seqs, loss_scale, d_nll, cs);
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (!rc && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&g->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc || ce != cudaSuccess || !g->exec) {   // not capturable here: keep the plain path for this configuration
+            cudaGetLastError();
+            g->exec = nullptr;
+            g->failed = 1;
+            if (getenv("FSMG_GRAPH_DEBUG")) fprintf(stderr, "[fsmg] step graph capture failed (rc=%d, %s)\n", rc, cudaGetErrorString(ce));
+            return enqueue_forward_backward(h, d_tokens, n_seqs, loss_scale, d_nll, s);
+        }
+        g->launches = h->launches;
+    }
+    FSMG_CUDA_OK(cudaGraphLaunch(g->exec, s));
+    h->launches = g->launches;
     return FSMG_OK;
 }
 
