@@ -325,6 +325,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape sh, EpiParams ep) {
     using L = SmemLayout<BN, CL>;
     constexpr int STAGES = L::STAGES;
+    // BN = 512 (cta_group::2 only): the pair's tile is 256 x 512, issued as two N = 256 MMAs per K step.  A is fetched once for the
+    // whole 512-wide N extent (the L2 -> SM operand traffic, not the tensor pipe, bounds the large-K GEMMs) and the accumulator
+    // fills all 512 TMEM columns, so it is single-buffered: only used when the K loop dwarfs the epilogue.
+    static_assert(BN <= 256 || CL == 2, "BN = 512 needs cta_group::2");
+    constexpr int NMMA = BN > 256 ? BN / 256 : 1;   // MMAs per K step
+    constexpr int MMA_N = BN / NMMA;                // N of one MMA
+    constexpr int ACC = BN > 256 ? 1 : 2;           // accumulator stages in TMEM (ACC * BN = 512 columns)
+    constexpr uint32_t B_PART = (MMA_N / CL) * BK * 2;   // bytes of one MMA's B operand in this CTA's stage
     extern __shared__ uint8_t smem_raw[];
     // keep the pointer in the shared address space (pointer arithmetic on the extern array, no integer round trip):
     // otherwise the staging accesses compile to generic LD/ST instead of LDS/STS
@@ -350,7 +358,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CL * NUM_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 1) { if (CL == 2) tmem_alloc_2sm(tmem_base_slot, 2 * BN); else tmem_alloc(tmem_base_slot, 2 * BN); }   // 2 accumulator stages
+    if (warp == 1) { if (CL == 2) tmem_alloc_2sm(tmem_base_slot, ACC * BN); else tmem_alloc(tmem_base_slot, ACC * BN); }   // accumulator stages
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();      // peer barriers are initialised before any multicast / remote arrive
@@ -393,12 +401,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         } else {
                             tma_load_2d_2sm(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
                         }
-                        if (B_MN) {
+                        // MMA j covers N columns [j * MMA_N, (j + 1) * MMA_N) of the tile; this CTA supplies its half of each
 #pragma unroll
-                            for (int jj = 0; jj < BN / 128; ++jj)
-                                tma_load_2d_2sm(sb + jj * 8192, &map_b, n_blk * BN + (cta_rank * (BN / 128) + jj) * 64, kb * BK, &full_bar[stage]);
-                        } else {
-                            tma_load_2d_2sm(sb, &map_b, kb * BK, n_blk * BN + cta_rank * (BN / 2), &full_bar[stage]);
+                        for (int j = 0; j < NMMA; ++j) {
+                            const int n0 = n_blk * BN + j * MMA_N + cta_rank * (MMA_N / 2);
+                            if (B_MN) {
+#pragma unroll
+                                for (int jj = 0; jj < MMA_N / 128; ++jj)
+                                    tma_load_2d_2sm(sb + j * B_PART + jj * 8192, &map_b, n0 + jj * 64, kb * BK, &full_bar[stage]);
+                            } else {
+                                tma_load_2d_2sm(sb + j * B_PART, &map_b, kb * BK, n0, &full_bar[stage]);
+                            }
                         }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -408,7 +421,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ===== MMA issuer (one thread; with cta_group::2 only the leader CTA of the pair issues, for both) =====
         if (lane == 0 && cta_rank == 0) {
-            constexpr uint32_t idesc = (CL == 2) ? make_idesc_full(256, BN, A_MN, B_MN) : make_idesc(BN, A_MN, B_MN);
+            constexpr uint32_t idesc = (CL == 2) ? make_idesc_full(256, MMA_N, A_MN, B_MN) : make_idesc(BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             WorkIter it(sh, cluster_id, n_clusters);
@@ -428,8 +441,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         // MN-major SW128: atom = 8 k-rows x 64 mn, SBO = 1024 B (next 8 k), LBO = 8192 B (next 64 mn), +2048 B per UMMA_K.
                         const uint64_t a_desc = A_MN ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
                         const uint64_t b_desc = B_MN ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-                        if (CL == 2) umma_f16_2sm(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);   // 256 x BN x 16 over both SMs
-                        else umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        if (CL == 2) {
+#pragma unroll
+                            for (int j = 0; j < NMMA; ++j)   // 256 x MMA_N x 16 over both SMs; (B_PART >> 4) = descriptor address units
+                                umma_f16_2sm(d_tmem + j * MMA_N, a_desc, b_desc + (uint64_t)(j * (B_PART >> 4)), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        } else {
+                            umma_f16(d_tmem, a_desc, b_desc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                        }
                     }
                     if (CL == 2) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);   // frees the stage in both CTAs
                     else umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
@@ -437,7 +455,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 }
                 if (CL == 2) umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);   // accumulators complete in both CTAs -> both epilogues
                 else umma_commit(&tmem_full[acc]);
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -474,21 +492,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     bias_r[i] = colb < sh.N ? ep.bias[colb] : 0.0f;
                 }
             }
-            float4 bias4[CHUNKS];
-            if (EPI == EPI_STORE) {   // bias of the 4 columns this lane writes out, fetched before the accumulator is awaited
-                const bool add_bias = ep.bias != nullptr && kb0 == 0;   // the piece that starts the K range carries the bias
-#pragma unroll
-                for (int cc = 0; cc < CHUNKS; ++cc) {
-                    const int colv = cb + cc * CW + 4 * (lane & 3);
-                    bias4[cc] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (add_bias) {
-                        if (colv + 3 < sh.N) bias4[cc] = *reinterpret_cast<const float4*>(ep.bias + colv);   // bias tensors are 256-B aligned
-                        else {
-                            bias4[cc].x = colv < sh.N ? ep.bias[colv] : 0.f; bias4[cc].y = colv + 1 < sh.N ? ep.bias[colv + 1] : 0.f;
-                            bias4[cc].z = colv + 2 < sh.N ? ep.bias[colv + 2] : 0.f; bias4[cc].w = colv + 3 < sh.N ? ep.bias[colv + 3] : 0.f;
-                        }
+            constexpr int NB4 = BN <= 256 ? CHUNKS : 1;   // BN = 512: fetched per chunk instead (register budget; its K loops are long)
+            float4 bias4[NB4];
+            const bool add_bias = ep.bias != nullptr && kb0 == 0;   // the piece that starts the K range carries the bias
+            auto fetch_bias = [&](int cc) -> float4 {               // bias of the 4 columns this lane writes out for chunk cc
+                const int colv = cb + cc * CW + 4 * (lane & 3);
+                float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (add_bias) {
+                    if (colv + 3 < sh.N) b = *reinterpret_cast<const float4*>(ep.bias + colv);   // bias tensors are 256-B aligned
+                    else {
+                        b.x = colv < sh.N ? ep.bias[colv] : 0.f; b.y = colv + 1 < sh.N ? ep.bias[colv + 1] : 0.f;
+                        b.z = colv + 2 < sh.N ? ep.bias[colv + 2] : 0.f; b.w = colv + 3 < sh.N ? ep.bias[colv + 3] : 0.f;
                     }
                 }
+                return b;
+            };
+            if constexpr (EPI == EPI_STORE && BN <= 256) {   // fetched before the accumulator is awaited
+#pragma unroll
+                for (int cc = 0; cc < CHUNKS; ++cc) bias4[cc] = fetch_bias(cc);
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
@@ -543,7 +564,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                             }
                         }
                     } else {
-                        const float4 b4 = bias4[cc];
+                        float4 b4;
+                        if constexpr (BN <= 256) b4 = bias4[cc]; else b4 = fetch_bias(cc);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) { v[k].x += b4.x; v[k].y += b4.y; v[k].z += b4.z; v[k].w += b4.w; }
                         if (ep.c_half) {
@@ -688,13 +710,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (lane == 0) {   // all epilogue warps (of both CTAs when paired) free the accumulator stage for the leader's MMA thread
                 if (CL == 2 && cta_rank == 1) mbar_arrive_remote(&tmem_empty[acc], 0); else mbar_arrive(&tmem_empty[acc]);
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (CL == 2) cluster_sync_all();      // no CTA exits while its peer may still read its smem / signal its barriers
-    if (warp == 1) { if (CL == 2) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN); }
+    if (warp == 1) { if (CL == 2) tmem_dealloc_2sm(tmem_base, ACC * BN); else tmem_dealloc(tmem_base, ACC * BN); }
 }
 
 // combine the per-(row, n-tile) (max, sumexp) partials: lse = M + log(sum_i s_i * exp(m_i - M)); nll = lse - tgt
@@ -912,6 +934,7 @@ struct TcContext {
     int enabled = 1;
     int cluster = 2;           // CTAs per cluster of the GEMM core (2 = cta_group::2 pairs, 1 = single-SM MMAs)
     int cluster_lse = 0;       // override for the logits + log-sum-exp GEMM (0 = same as `cluster`)
+    int wide = 1;              // 256 x 512 pair tiles for plain-store GEMMs with long K loops (FSMG_WIDE=0 disables)
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
     int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
@@ -934,6 +957,8 @@ static inline int tc_init(TcContext& c) {
     c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
     const char* envcl = getenv("FSMG_CLUSTER_LSE");
     c.cluster_lse = envcl ? atoi(envcl) : 0;
+    const char* envw = getenv("FSMG_WIDE");
+    c.wide = envw ? atoi(envw) : 1;
     const char* envs = getenv("FSMG_STREAMK");
     c.streamk = envs ? atoi(envs) : 1;
     const char* envp = getenv("FSMG_LSTM_PAIR");
@@ -953,6 +978,8 @@ static inline int tc_init(TcContext& c) {
                                       tc::SmemLayout<BN, 1>::TOTAL));                                                    \
     FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<BN, EPI, AM, BMN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                       tc::SmemLayout<BN, 2>::TOTAL))
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<512, tc::EPI_STORE, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<512, 2>::TOTAL));
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<512, tc::EPI_STORE, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<512, 2>::TOTAL));
     FSMG_SET_SMEM(256, tc::EPI_STORE, false, false);
     FSMG_SET_SMEM(256, tc::EPI_STORE, true, true);
     FSMG_SET_SMEM(128, tc::EPI_STORE, false, false);
@@ -1000,15 +1027,17 @@ struct TcPlan {
     int cl;   // cluster size (1 or 2)
 };
 
-static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split, int cl_pref = 0) {
+static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split, int cl_pref = 0, bool allow_wide = false) {
     TcPlan p;
     p.bn = (N > 128) ? 256 : 128;
     tc::GemmShape& sh = p.sh;
     sh.M = M; sh.N = N; sh.K = K;
     sh.n_m = cdiv(M, tc::BM);
-    sh.n_n = cdiv(N, p.bn);
     sh.kb_total = cdiv(K, tc::BK);
     p.cl = ((cl_pref ? cl_pref : c.cluster) == 2 && sh.n_m >= 2) ? 2 : 1;     // pairs need two M tiles that share a B tile
+    // 256 x 512 pair tiles (A fetched once per 512 columns, single-buffered accumulator): long K loops only, little N padding
+    if (allow_wide && c.wide && p.cl == 2 && N >= 384 && sh.kb_total >= 64 && cdiv(N, 512) * 512 - N < 128) p.bn = 512;
+    sh.n_n = cdiv(N, p.bn);
     sh.n_mp = cdiv(sh.n_m, p.cl);
     const int slots = c.num_sms / p.cl;                  // concurrently resident clusters
     int tiles = sh.n_mp * sh.n_n;                        // cluster-tiles
@@ -1071,7 +1100,10 @@ static inline int tc_launch(const TcContext& c, const TcPlan& p, const CUtensorM
     if constexpr (EPI == tc::EPI_LSE || EPI == tc::EPI_SCATTER) {
         rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
     } else {
-        if (!mn) rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
+        if (p.bn == 512) {   // cta_group::2 only
+            rc = !mn ? tc_launch_kernel(tc::tc_gemm_kernel<512, EPI, false, false, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s)
+                     : tc_launch_kernel(tc::tc_gemm_kernel<512, EPI, true, true, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s);
+        } else if (!mn) rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
         else rc = (p.bn == 256) ? FSMG_GO(256, true) : FSMG_GO(128, true);
     }
 #undef FSMG_GO
@@ -1084,7 +1116,7 @@ static inline int tc_make_maps(const TcContext& c, const GemmArgs& g, bool mn, i
     int rc;
     if (!mn) {
         if ((rc = make_map_f16(c, ma, g.A, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda, tc::BK, tc::BM))) return rc;
-        if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, tc::BK, (uint32_t)(bn / cl)))) return rc;   // each CTA of a pair fetches half of B
+        if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb, tc::BK, (uint32_t)((bn > 256 ? 256 : bn) / cl)))) return rc;   // each CTA of a pair fetches half of each MMA's B
     } else {
         if ((rc = make_map_f16(c, ma, g.A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda, 64, tc::BK))) return rc;
         if ((rc = make_map_f16(c, mb, g.B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb, 64, tc::BK))) return rc;
@@ -1096,7 +1128,7 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
     (void)b_mn;
     if (!c.ready) return set_error(-3, "tcgen05 context not initialised");
     const bool can_split = !g.c_half && !g.accumulate;   // split-K partials are combined with fp32 atomics
-    TcPlan p = tc_plan(c, g.M, g.N, g.K, can_split);
+    TcPlan p = tc_plan(c, g.M, g.N, g.K, can_split, 0, true);
     tc::EpiParams ep;
     memset(&ep, 0, sizeof ep);
     ep.C = g.C; ep.ldc = g.ldc; ep.bias = g.bias; ep.alpha = g.alpha; ep.c_half = g.c_half; ep.accumulate = g.accumulate;

@@ -11,6 +11,8 @@ SHAPES = [
     # (M, N, K)
     (128, 256, 64), (128, 128, 64), (256, 512, 512), (200, 300, 136), (45, 800, 248), (1440, 2048, 512),
     (130, 10008, 512), (2304, 512, 10008), (512, 2048, 9000), (77, 40, 72),
+    # long-K plain-store GEMMs take the 256 x 512 pair tiles (two N = 256 MMAs per K step): exact, ragged N, ragged M
+    (1000, 512, 4096), (300, 1000, 4104), (3000, 1024, 8192),
 ]
 
 
