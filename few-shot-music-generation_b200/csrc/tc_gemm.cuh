@@ -11,6 +11,7 @@
 // (until the persistent kernel takes over), K5+K7 projection with fused online log-sum-exp / NLL,
 // K8 dgrad / wgrad GEMMs.
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -268,6 +269,7 @@ struct GemmShape {
     int n_mp;               // M tiles per cluster-tile row = ceil(n_m / CL): a cluster of CL CTAs owns CL consecutive M tiles of one N tile
     int kb_per_split;       // k-blocks per split
     int kb_total;
+    int astat_s;            // A-stationary schedule: N ranges per M pair-block (items = n_mp * astat_s)
 };
 
 // Work iterator shared by the three warp roles.  mode 0: cluster-tiles (optionally K-split) strided over the clusters;
@@ -305,25 +307,66 @@ struct WorkIter {
     }
 };
 
-template <int BN, int CL>
+// A-stationary schedule (logits GEMM, K <= 512): an item is (M pair-block, contiguous range of N tiles); the pair keeps its 256 x K
+// block of A resident in smem for the whole item and streams only B.  Items are strided over the pairs.
+struct AstatIter {
+    int item, total, stride, m_pb, n_cur, n_hi;
+    bool first, last;      // first / last N tile of the current item
+    __device__ __forceinline__ AstatIter(const GemmShape& sh, int cluster_id, int n_clusters) {
+        stride = n_clusters;
+        item = cluster_id - n_clusters;
+        total = sh.n_mp * sh.astat_s;
+        m_pb = 0; n_cur = 0; n_hi = 0; first = false; last = false;
+    }
+    __device__ __forceinline__ bool next(const GemmShape& sh, int& tile_mn, int& kb0, int& kb1) {
+        if (n_cur >= n_hi) {
+            item += stride;
+            if (item >= total) return false;
+            m_pb = item / sh.astat_s;
+            const int sidx = item - m_pb * sh.astat_s;
+            n_cur = (sidx * sh.n_n) / sh.astat_s;
+            n_hi = ((sidx + 1) * sh.n_n) / sh.astat_s;
+            first = true;
+        } else {
+            first = false;
+        }
+        last = (n_cur + 1 == n_hi);
+        tile_mn = n_cur * sh.n_mp + m_pb;
+        kb0 = 0; kb1 = sh.kb_total;
+        ++n_cur;
+        return true;
+    }
+};
+struct WorkIterFlags : WorkIter {   // same interface for the streaming schedule (flags unused)
+    bool first = true, last = true;
+    __device__ __forceinline__ WorkIterFlags(const GemmShape& sh, int cluster_id, int n_clusters) : WorkIter(sh, cluster_id, n_clusters) {}
+};
+
+constexpr int ASTAT_KB = 8;   // resident A panels (64 k each): K <= 512
+
+template <int BN, int CL, bool ASTAT = false>
 struct SmemLayout {
     static constexpr int A_BYTES = BM * BK * 2;              // 16 KB
     static constexpr int B_BYTES = (BN / CL) * BK * 2;       // CL = 2 (cta_group::2): each CTA of the pair holds half of the B tile
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;    // 48 / 32 / 24 KB
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES > 8 ? 8 : (192 * 1024) / STAGE_BYTES;
-    static constexpr int BAR_BYTES = 256;
+    static constexpr int RES_BYTES = ASTAT ? ASTAT_KB * A_BYTES : 0;       // A-stationary: this CTA's 128 x 512 block of A stays resident
+    static constexpr int STAGE_BYTES = ASTAT ? B_BYTES : A_BYTES + B_BYTES;    // 48 / 32 / 24 KB (16 KB when only B streams)
+    static constexpr int RING = 192 * 1024 - RES_BYTES;
+    static constexpr int STAGES = RING / STAGE_BYTES > 8 ? 8 : RING / STAGE_BYTES;
+    static constexpr int BAR_BYTES = 512;
     static constexpr int EPI_BYTES = NUM_EPI_WARPS * EPI_STAGE_BYTES;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
+    static constexpr int TOTAL = RES_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 // CL = 2: the two CTAs of a cluster issue ONE tcgen05.mma.cta_group::2 of 256 x BN x 16 per K step: each CTA streams its own 128
 // rows of A and only HALF of the B tile, the tensor cores read both CTAs' shared memory.  The K-streaming mainloop is bound by the
 // bytes that must LAND in each SM's smem (measured ~40 B/clk/SM; a 1-SM 128 x 256 tile needs 96 B/clk at full tensor rate) —
 // TMA multicast (the previous CL = 2 scheme) cut L2 reads but not that ingest; the 2-SM MMA cuts it by a third.
-template <int BN, int EPI, bool A_MN, bool B_MN, int CL>
+template <int BN, int EPI, bool A_MN, bool B_MN, int CL, bool ASTAT = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape sh, EpiParams ep) {
-    using L = SmemLayout<BN, CL>;
+    using L = SmemLayout<BN, CL, ASTAT>;
+    using Iter = std::conditional_t<ASTAT, AstatIter, WorkIterFlags>;
+    static_assert(!ASTAT || (CL == 2 && !A_MN && !B_MN && BN <= 256), "A-stationary schedule: K-major operands, cta_group::2");
     constexpr int STAGES = L::STAGES;
     // BN = 512 (cta_group::2 only): the pair's tile is 256 x 512, issued as two N = 256 MMAs per K step.  A is fetched once for the
     // whole 512-wide N extent (the L2 -> SM operand traffic, not the tensor pipe, bounds the large-K GEMMs) and the accumulator
@@ -337,12 +380,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // keep the pointer in the shared address space (pointer arithmetic on the extern array, no integer round trip):
     // otherwise the staging accesses compile to generic LD/ST instead of LDS/STS
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* epi_smem = smem + STAGES * L::STAGE_BYTES;
+    uint8_t* res_a = smem;                       // ASTAT: ASTAT_KB resident A panels (128 rows x 64 k each)
+    uint8_t* ring = smem + L::RES_BYTES;
+    uint8_t* epi_smem = ring + STAGES * L::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + L::EPI_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* a_full = tmem_empty + 2;          // [ASTAT_KB] ASTAT: panel kb of the current item has landed (leader: both CTAs' bytes)
+    uint64_t* a_empty = a_full + ASTAT_KB;      // [ASTAT_KB] ASTAT: the item's last MMAs on panel kb have retired
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_empty + ASTAT_KB);
+    static_assert((2 * 8 + 4 + 2 * ASTAT_KB) * 8 + 8 <= L::BAR_BYTES, "barrier block");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta_rank = (CL == 2) ? (int)cluster_ctarank() : 0;
@@ -356,6 +404,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // empty / tmem_full are signalled in both CTAs by the leader's multicast tcgen05.commit
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CL * NUM_EPI_WARPS); }
+        if (ASTAT) for (int i = 0; i < ASTAT_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         fence_barrier_init();
     }
     if (warp == 1) { if (CL == 2) tmem_alloc_2sm(tmem_base_slot, ACC * BN); else tmem_alloc(tmem_base_slot, ACC * BN); }   // accumulator stages
@@ -369,15 +418,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            WorkIter it(sh, cluster_id, n_clusters);
+            uint32_t a_phase = 0;
+            Iter it(sh, cluster_id, n_clusters);
             int tile_mn, kb0, kb1;
             while (it.next(sh, tile_mn, kb0, kb1)) {
                 const int m_blk = (tile_mn % sh.n_mp) * CL + cta_rank, n_blk = tile_mn / sh.n_mp;
+                if (ASTAT && it.first) {
+                    // new item: refill the resident A panels.  Panel kb is released by the previous item's last tile as soon as its
+                    // MMAs on that panel retire, so the refill overlaps that tile's remaining K steps and its epilogue.
+                    for (int kb = 0; kb < sh.kb_total; ++kb) {
+                        mbar_wait(&a_empty[kb], a_phase ^ 1);
+                        if (cta_rank == 0) mbar_expect_tx(&a_full[kb], 2 * L::A_BYTES);
+                        tma_load_2d_2sm(res_a + kb * L::A_BYTES, &map_a, kb * BK, m_blk * BM, &a_full[kb]);
+                    }
+                    a_phase ^= 1;
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    uint8_t* sb = sa + L::A_BYTES;
-                    if (CL == 1) {
+                    uint8_t* sa = ring + stage * L::STAGE_BYTES;
+                    uint8_t* sb = ASTAT ? sa : sa + L::A_BYTES;
+                    if (ASTAT) {   // only this CTA's half of the B tile streams
+                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                        tma_load_2d_2sm(sb, &map_b, kb * BK, n_blk * BN + cta_rank * (BN / 2), &full_bar[stage]);
+                    } else if (CL == 1) {
                         mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                         if (A_MN) {
 #pragma unroll
@@ -424,17 +487,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             constexpr uint32_t idesc = (CL == 2) ? make_idesc_full(256, MMA_N, A_MN, B_MN) : make_idesc(BN, A_MN, B_MN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            WorkIter it(sh, cluster_id, n_clusters);
+            uint32_t a_phase = 0;
+            Iter it(sh, cluster_id, n_clusters);
             int tile_mn, kb0, kb1;
             while (it.next(sh, tile_mn, kb0, kb1)) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
+                    if (ASTAT && it.first) mbar_wait(&a_full[kb], a_phase);   // the item's A panel kb is resident (both CTAs)
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t sb = sa + L::A_BYTES;
+                    const uint32_t sa = ASTAT ? smem_u32(res_a + kb * L::A_BYTES) : smem_u32(ring + stage * L::STAGE_BYTES);
+                    const uint32_t sb = ASTAT ? smem_u32(ring + stage * L::STAGE_BYTES) : sa + L::A_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // K-major SW128: atom = 8 rows x 128 B, SBO = 1024 B, +32 B per UMMA_K inside the swizzle row.
@@ -451,8 +516,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     if (CL == 2) umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);   // frees the stage in both CTAs
                     else umma_commit(&empty_bar[stage]);        // smem slot reusable once these MMAs retire
+                    if (ASTAT && it.last) umma_commit_2sm_mc(&a_empty[kb], (uint16_t)0x3);   // panel kb may be refilled for the next item
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (ASTAT && it.last) a_phase ^= 1;
                 if (CL == 2) umma_commit_2sm_mc(&tmem_full[acc], (uint16_t)0x3);   // accumulators complete in both CTAs -> both epilogues
                 else umma_commit(&tmem_full[acc]);
                 if (++acc == ACC) { acc = 0; acc_phase ^= 1; }
@@ -471,7 +538,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint4* sh4 = reinterpret_cast<uint4*>(stg);              // fp16 staging: 32 rows x 2 uint4, slot c2 ^ ((row >> 2) & 1)
         float* bias_s = reinterpret_cast<float*>(stg + 1024);    // EPI_LSE: bias of this warp's GCOLS columns
         int acc = 0; uint32_t acc_phase = 0;
-        WorkIter it(sh, cluster_id, n_clusters);
+        Iter it(sh, cluster_id, n_clusters);
         int tile_mn, kb0, kb1;
         while (it.next(sh, tile_mn, kb0, kb1)) {
             const int m_blk = (tile_mn % sh.n_mp) * CL + cta_rank, n_blk = tile_mn / sh.n_mp;
@@ -934,6 +1001,7 @@ struct TcContext {
     int enabled = 1;
     int cluster = 2;           // CTAs per cluster of the GEMM core (2 = cta_group::2 pairs, 1 = single-SM MMAs)
     int cluster_lse = 0;       // override for the logits + log-sum-exp GEMM (0 = same as `cluster`)
+    int astat = 1;             // A-stationary schedule for the logits GEMM when K <= 512 (FSMG_ASTAT=0 disables)
     int wide = 1;              // 256 x 512 pair tiles for plain-store GEMMs with long K loops (FSMG_WIDE=0 disables)
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
     int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
@@ -957,6 +1025,8 @@ static inline int tc_init(TcContext& c) {
     c.cluster = envc ? (atoi(envc) == 1 ? 1 : 2) : 2;
     const char* envcl = getenv("FSMG_CLUSTER_LSE");
     c.cluster_lse = envcl ? atoi(envcl) : 0;
+    const char* enva = getenv("FSMG_ASTAT");
+    c.astat = enva ? atoi(enva) : 1;
     const char* envw = getenv("FSMG_WIDE");
     c.wide = envw ? atoi(envw) : 1;
     const char* envs = getenv("FSMG_STREAMK");
@@ -985,6 +1055,7 @@ static inline int tc_init(TcContext& c) {
     FSMG_SET_SMEM(128, tc::EPI_STORE, false, false);
     FSMG_SET_SMEM(128, tc::EPI_STORE, true, true);
     FSMG_SET_SMEM(256, tc::EPI_LSE, false, false);
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<256, tc::EPI_LSE, false, false, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<256, 2, true>::TOTAL));
     FSMG_SET_SMEM(256, tc::EPI_SCATTER, false, false);
     FSMG_SET_SMEM(128, tc::EPI_SCATTER, false, false);
     FSMG_SET_SMEM(128, tc::EPI_LSE, false, false);
@@ -1174,7 +1245,8 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     memset(&g, 0, sizeof g);
     g.M = mc; g.N = V1; g.K = H; g.A = hc; g.lda = ldh; g.B = WsT16; g.ldb = ldw;
     if (!tc_operands_ok(g.A, g.lda) || !tc_operands_ok(g.B, g.ldb)) return set_error(-1, "projection operands not TMA-aligned");
-    TcPlan p = tc_plan(c, mc, V1, H, false, c.cluster_lse);
+    const bool astat = c.astat && H <= tc::ASTAT_KB * tc::BK && V1 > 128 && mc > tc::BM;
+    TcPlan p = tc_plan(c, mc, V1, H, false, astat ? 2 : c.cluster_lse);
     tc::EpiParams ep;
     memset(&ep, 0, sizeof ep);
     ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 4 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
@@ -1183,6 +1255,24 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     CUtensorMap ma, mb;
     int rc = tc_make_maps(c, g, false, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;
+    if (astat && p.cl == 2 && p.bn == 256) {
+        // A-stationary schedule: items = (M pair-block, 1/S of the N tiles); pick S for the fewest tile-times on the busiest pair
+        const int slots = c.num_sms / 2;
+        int best_s = 1; double best = 1e30;
+        for (int sp = 1; sp <= 16 && sp <= p.sh.n_n; ++sp) {
+            const int items = p.sh.n_mp * sp;
+            const double cost = (double)cdiv(items, slots) * (cdiv(p.sh.n_n, sp) + 0.25);   // + A refill / pipeline restart per item
+            if (cost < best - 1e-9) { best = cost; best_s = sp; }
+        }
+        p.sh.astat_s = best_s;
+        p.sh.streamk = 0; p.sh.n_s = 1;
+        const int items = p.sh.n_mp * best_s;
+        p.grid = (items < slots ? items : slots) * 2;
+        rc = tc_launch_kernel(tc::tc_gemm_kernel<256, tc::EPI_LSE, false, false, 2, true>, p, tc::SmemLayout<256, 2, true>::TOTAL, ma, mb, ep, s);
+        if (rc) return rc;
+        FSMG_LAUNCH_OK();
+        return 0;
+    }
     return tc_launch<tc::EPI_LSE>(c, p, ma, mb, false, ep, s);
 }
 
