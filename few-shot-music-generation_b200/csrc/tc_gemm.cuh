@@ -1004,6 +1004,7 @@ struct TcContext {
     int astat = 1;             // A-stationary schedule for the logits GEMM when K <= 512 (FSMG_ASTAT=0 disables)
     int wide = 1;              // 256 x 512 pair tiles for plain-store GEMMs with long K loops (FSMG_WIDE=0 disables)
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
+    int lstm_split = 1;        // forward recurrent kernel: two interleaved half-groups per CTA (FSMG_LSTM_SPLIT=0: one lock-step group)
     int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
 };
@@ -1033,6 +1034,8 @@ static inline int tc_init(TcContext& c) {
     c.streamk = envs ? atoi(envs) : 1;
     const char* envp = getenv("FSMG_LSTM_PAIR");
     c.lstm_pair = envp ? atoi(envp) : 1;   // bit 0: backward (measured 2.64 -> 1.99 ms), bit 1: forward (neutral)
+    const char* envsp = getenv("FSMG_LSTM_SPLIT");
+    c.lstm_split = envsp ? atoi(envsp) : 1;
     const char* envl = getenv("FSMG_LSTM_CLUSTER");
     c.lstm_cluster = envl ? atoi(envl) : 1;
     int dev = 0;

@@ -95,6 +95,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 #define FSMG_TR(step, slot)                                                                      \
@@ -415,6 +420,243 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     __syncthreads();
     if (CLS > 1 || PAIR) cluster_sync_all();
     if (warp == 1) { if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// =====================================================================================================
+// forward, split schedule: the group's rows are cut into two independent HALVES (own progress counter, own TMEM double
+// buffer, own epilogue warps); the producer and the MMA thread serve them alternately.  While one half waits for its
+// exchange (publish -> counter -> TMA round trip through L2, ~4 us) the other half's loads, MMAs and cell epilogue
+// run, so the per-step latency chain of one half hides behind the work of the other.  The epilogue additionally splits
+// a row's U units over two threads (16 warps: half x unit slice x TMEM quadrant), halving its dependent MUFU chain.
+// =====================================================================================================
+constexpr int LSTM_SPLIT_THREADS = 64 + 512;
+
+template <int U>
+__global__ void __launch_bounds__(LSTM_SPLIT_THREADS, 1)
+lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h, LstmParams p) {
+    constexpr int NCOL = 4 * U;                 // accumulator columns of one half's buffer (UMMA N)
+    constexpr int CHUNK_W = NCOL * 128;
+    constexpr int US = U / 2;                   // units per epilogue thread
+    static_assert(4 * NCOL <= 512, "two halves x two buffers must fit the 512 TMEM columns");
+    const int KC = p.H / 64;
+    const int W_BYTES = KC * CHUNK_W;
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = p.stage_bytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem;
+    uint8_t* sA = sW + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LSTM_MAX_DYN - 1024 - 256);
+    uint64_t* full_bar = bars;                  // [8]
+    uint64_t* empty_bar = bars + 8;             // [8]
+    uint64_t* w_bar = bars + 16;
+    uint64_t* tmem_full = bars + 17;            // [2] per half
+    uint64_t* pre_ready = bars + 19;            // [2][2] per half, per TMEM buffer parity
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
+    const int group_row0 = p.row_offset + g * p.rows_per_group;
+    const int group_rows = min(p.rows_per_group, p.row_offset + p.n_rows - group_row0);
+    const int hr = p.box_rows;                  // rows per half (multiple of 8, <= 128)
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_h);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(w_bar, 1);
+        for (int i = 0; i < 2; ++i) mbar_init(&tmem_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&pre_ready[i], 8);   // 2 unit slices x 4 quadrant warps
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)W_BYTES);
+            for (int kc = 0; kc < KC; ++kc)
+                for (int q = 0; q < 4; ++q)
+                    tma_load_2d(sW + kc * CHUNK_W + q * U * 128, &map_w, kc * 64, q * p.H + j * U, w_bar);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t box_bytes = (uint32_t)hr * 128u;
+            for (int t = 1; t < p.T; ++t) {
+                const int need = p.ctas_per_group * t;
+                for (int hs_ = 0; hs_ < 2; ++hs_) {
+                    int* counter = p.counters + 2 * g + hs_;
+                    while (ld_acquire(counter) < need) { }
+                    if (hs_ == 0) FSMG_TR(t, 0);
+                    fence_proxy_async_all();
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], box_bytes);
+                        tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kc * 64, group_row0 + hs_ * hr, t - 1, &full_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (hs_ == 0) FSMG_TR(t, 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(NCOL, false, false);
+            mbar_wait(w_bar, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            uint32_t pr_phase[4] = {0, 0, 0, 0};
+            for (int t = 1; t < p.T; ++t) {
+                for (int hs_ = 0; hs_ < 2; ++hs_) {
+                    const int b = hs_ * 2 + (t & 1);
+                    mbar_wait(&pre_ready[b], pr_phase[b]);     // pre[t] of this half is staged in its buffer: every MMA accumulates
+                    pr_phase[b] ^= 1;
+                    tc_fence_after();
+                    const uint32_t d_buf = tmem_base + (uint32_t)(b * NCOL);
+                    for (int kc = 0; kc < KC; ++kc) {
+                        mbar_wait(&full_bar[stage], phase);
+                        if (kc == 0 && hs_ == 0) FSMG_TR(t, 2);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
+                        const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_f16(d_buf, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, 1u);
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(&tmem_full[hs_]);
+                    if (hs_ == 0) FSMG_TR(t, 3);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 16 warps = half (2) x unit slice (2) x TMEM lane quadrant (4); thread <-> one row, US units
+        const int quad = warp & 3;
+        const int idx = (warp - 2) >> 2;
+        const int hs_ = idx >> 1, us = idx & 1;
+        const int row_base = group_row0 + hs_ * hr;
+        const int rows = max(0, min(hr, group_rows - hs_ * hr));
+        const int lrow = quad * 32 + lane;
+        const bool ok = lrow < rows;
+        const int ucol = j * U + us * US;                     // first hidden unit of this thread
+        int* counter = p.counters + 2 * g + hs_;
+        const bool tracer = (hs_ == 0 && us == 0 && quad == 0 && lane == 0);
+        float c_state[US];
+#pragma unroll
+        for (int u = 0; u < US; ++u) c_state[u] = 0.0f;
+        uint32_t tf_phase = 0;
+        auto stage_pre = [&](int t) {
+            const __half* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * p.G4p + ucol;
+            const uint32_t t_row = tmem_base + (uint32_t)((hs_ * 2 + (t & 1)) * NCOL) + us * US + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t rr[US];
+#pragma unroll
+                for (int e = 0; e < US; e += 8) {
+                    uint4 raw = ok ? __ldcs(reinterpret_cast<const uint4*>(pre + q * p.H + e)) : make_uint4(0, 0, 0, 0);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        const float2 f = __half22float2(h2[w]);
+                        rr[e + 2 * w] = __float_as_uint(f.x);
+                        rr[e + 2 * w + 1] = __float_as_uint(f.y);
+                    }
+                }
+                if constexpr (US == 16) tmem_st16(t_row + q * U, rr); else tmem_st8(t_row + q * U, rr);
+            }
+            tmem_st_wait();
+        };
+        stage_pre(0);
+        for (int t = 0; t < p.T; ++t) {
+            if (t + 1 < p.T) {
+                stage_pre(t + 1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&pre_ready[hs_ * 2 + ((t + 1) & 1)]);
+                if (tracer) FSMG_TR(t, 4);
+                if (t + 2 < p.T && ok) {
+                    const __half* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * p.G4p + ucol;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
+                }
+            }
+            if (t > 0) {
+                mbar_wait(&tmem_full[hs_], tf_phase);
+                tf_phase ^= 1;
+                tc_fence_after();
+            }
+            if (tracer) FSMG_TR(t, 5);
+            const int64_t r = (int64_t)t * p.N + row_base + lrow;
+            uint4 g_stash[US / 8][4];
+            float4 c_stash[US / 8][2];
+            {
+                const uint32_t t_row = tmem_base + (uint32_t)((hs_ * 2 + (t & 1)) * NCOL) + us * US + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+                for (int u0 = 0; u0 < US; u0 += 8) {
+                    float acc[4][8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t rr[8];
+                        tmem_ld8(t_row + q * U + u0, rr);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[q][e] = __uint_as_float(rr[e]);
+                    }
+                    tmem_ld_wait();
+                    __align__(16) __half hq[4][8];
+                    __align__(16) __half hh[8];
+                    float cn[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        // 5 ex2 + 3 rcp per unit: sigmoid(a) and tanh(b) share one reciprocal of (1+e^-a)(1+e^-2b); exponents clamped at 2^57
+                        const float ea = fast_ex2(fminf(-1.4426950408889634f * acc[0][e], 57.0f));
+                        const float eb = fast_ex2(fminf(-2.8853900817779268f * acc[1][e], 57.0f));
+                        const float ef = fast_ex2(fminf(-1.4426950408889634f * (acc[2][e] + 1.0f), 57.0f));   // forget_bias = 1 (A.2)
+                        const float eo = fast_ex2(fminf(-1.4426950408889634f * acc[3][e], 57.0f));
+                        const float r1 = __fdividef(1.0f, (1.0f + ea) * (1.0f + eb));
+                        const float i_ = r1 * (1.0f + eb);
+                        const float j_ = (1.0f - eb) * (r1 * (1.0f + ea));
+                        const float f_ = __fdividef(1.0f, 1.0f + ef);
+                        const float cv = c_state[u0 + e] * f_ + i_ * j_;
+                        c_state[u0 + e] = cv;
+                        cn[e] = cv;
+                        const float ec = fast_ex2(fminf(-2.8853900817779268f * cv, 57.0f));
+                        const float r2 = __fdividef(1.0f, (1.0f + ec) * (1.0f + eo));
+                        const float o_ = r2 * (1.0f + ec);
+                        const float tc_ = (1.0f - ec) * (r2 * (1.0f + eo));
+                        hq[0][e] = __float2half_rn(i_); hq[1][e] = __float2half_rn(j_);
+                        hq[2][e] = __float2half_rn(f_); hq[3][e] = __float2half_rn(o_);
+                        hh[e] = __float2half_rn(tc_ * o_);
+                    }
+                    if (ok) *reinterpret_cast<uint4*>(p.hs + r * p.Hp + ucol + u0) = *reinterpret_cast<uint4*>(hh);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) g_stash[u0 / 8][q] = *reinterpret_cast<uint4*>(hq[q]);
+                    c_stash[u0 / 8][0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                    c_stash[u0 / 8][1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                }
+            }
+            // publish this half: barrier over its 8 warps, then ONE gpu-scope release
+            tc_fence_before();
+            if (tracer) FSMG_TR(t, 6);
+            named_bar_sync(1 + hs_, 256);
+            if (us == 0 && quad == 0 && lane == 0) { if (tracer) FSMG_TR(t, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(t, 8); }
+            if (ok) {
+                __half* gout = p.gates + r * p.G4p + ucol;
+                float* cdst = p.c + r * p.H + ucol;
+#pragma unroll
+                for (int u0 = 0; u0 < US; u0 += 8) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(gout + q * p.H + u0) = g_stash[u0 / 8][q];
+                    *reinterpret_cast<float4*>(cdst + u0) = c_stash[u0 / 8][0];
+                    *reinterpret_cast<float4*>(cdst + u0 + 4) = c_stash[u0 / 8][1];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // =====================================================================================================
@@ -846,6 +1088,14 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
     if (rc) return rc;
     rc = make_map_f16_3d(c, &mh, hs, (uint64_t)H, (uint64_t)N, (uint64_t)T, (uint64_t)Hp, (uint64_t)N * Hp, 64, (uint32_t)pl.box_rows);
     if (rc) return rc;
+    // split schedule (default): two independently progressing halves per group hide each other's exchange latency
+    const bool split = c.lstm_split && !pl.pair && pl.cls == 1 && pl.rows_per_group >= 16;
+    const int half_rows = (int)round_up(cdiv(pl.rows_per_group, 2), 8);
+    CUtensorMap mh_split = mh;
+    if (split) {
+        rc = make_map_f16_3d(c, &mh_split, hs, (uint64_t)H, (uint64_t)N, (uint64_t)T, (uint64_t)Hp, (uint64_t)N * Hp, 64, (uint32_t)half_rows);
+        if (rc) return rc;
+    }
     for (int off = 0; off < N; off += pl.rows_per_launch) {
         int n_rows = N - off < pl.rows_per_launch ? N - off : pl.rows_per_launch;
         int G = cdiv(n_rows, pl.rows_per_group);
@@ -861,7 +1111,15 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
         const CUtensorMap& mx = mh;
         const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
         if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
-        FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc, true);
+        if (split) {
+            // two independent halves per group (own counters: 2 per group), one CTA per (group, unit slice)
+            p.box_rows = half_rows;
+            lstm_ring(w_bytes, half_rows, 1, &p.stage_bytes, &p.stages);
+            if (pl.U == 32) rc = lstm_launch(tc::lstm_fwd_split_kernel<32>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
+            else rc = lstm_launch(tc::lstm_fwd_split_kernel<16>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
+        } else {
+            FSMG_LSTM_DISPATCH(lstm_fwd_persistent_kernel, rc, true);
+        }
         if (trace && !rc) lstm_trace_dump(c, "lstm_fwd_persistent", s);
         if (rc) return rc;
     }
