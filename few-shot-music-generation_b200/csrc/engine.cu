@@ -617,7 +617,7 @@ int fsmg_create(const fsmg_config* cfg, const char* scope_name, fsmg_handle** ou
     h->V = cfg->vocab; h->V1 = cfg->vocab + 1; h->E = cfg->embed; h->H = cfg->hidden; h->L = cfg->layers;
     h->T = cfg->max_len; h->Nmax = cfg->max_seqs;
     h->Ep = (int)round_up(h->E, 8); h->Hp = (int)round_up(h->H, 8); h->G4 = 4 * h->H; h->G4p = (int)round_up(h->G4, 8);
-    h->Vp = (int)round_up(h->V1, 8);
+    h->Vp = (int)round_up(h->V1, 16);   // fp16 logits rows start on 32-byte boundaries (256-bit stores in the LSE epilogue)
     // flat parameter layout, TF get_vars() order (reference tf_model.py:99-104)
     int64_t off = 0;
     auto add = [&](const std::string& name, int rows, int cols) {

@@ -735,35 +735,27 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     run_sum = run_sum * __expf(run_max - nmax) + ((sa0 + sa1) + (sa2 + sa3));
                     run_max = nmax;
-                    if (ep.logits16) {
-                        // fp16 logits for the backward: staged through smem (32-B rows) -> 16 rows x 32 B per store instruction
+                    if (ep.logits16 && row_ok) {
+                        // fp16 logits for the backward: this lane's 16 columns are 32 contiguous bytes of its row = one full sector:
+                        // ONE 256-bit store, no smem transpose (the staged variant spent a third of the chunk's stall samples on
+                        // STS -> syncwarp -> LDS -> STG)
+                        __half* dst = ep.logits16 + (int64_t)row * ep.ld16 + col0;
+                        uint32_t pk[8];
 #pragma unroll
-                        for (int c2 = 0; c2 < 2; ++c2) {
-                            __align__(16) __half2 hh[4];
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) hh[q] = __floats2half2_rn(v[8 * c2 + 2 * q], v[8 * c2 + 2 * q + 1]);
-                            sh4[lane * 2 + (c2 ^ ((lane >> 2) & 1))] = *reinterpret_cast<uint4*>(hh);
+                        for (int q = 0; q < 8; ++q) {
+                            const __half2 h2 = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+                            pk[q] = *reinterpret_cast<const uint32_t*>(&h2);
                         }
-                        __syncwarp();
-                        const int c2 = lane & 1;
-                        const int colh = col0 + 8 * c2;
+                        if (full && ep.vec_ok) {      // host-checked: base 32-B aligned, ld16 % 16 == 0
+                            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                                         "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                                         : "memory");
+                        } else {
+                            const __half* ph = reinterpret_cast<const __half*>(pk);
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int rr = 16 * k + (lane >> 1);
-                            const int grow = row_w0 + rr;
-                            uint4 pk = sh4[rr * 2 + (c2 ^ ((rr >> 2) & 1))];
-                            if (grow < sh.M) {
-                                __half* dst = ep.logits16 + (int64_t)grow * ep.ld16 + colh;
-                                if (colh + 8 <= sh.N) *reinterpret_cast<uint4*>(dst) = pk;   // ld16 % 8 == 0, col0 % 16 == 0 -> 16-B aligned
-                                else {
-                                    const __half* ph = reinterpret_cast<const __half*>(&pk);
-#pragma unroll
-                                    for (int e = 0; e < 8; ++e)
-                                        if (colh + e < sh.N) dst[e] = ph[e];
-                                }
-                            }
+                            for (int e = 0; e < CW; ++e)
+                                if (col0 + e < sh.N) dst[e] = ph[e];
                         }
-                        __syncwarp();
                     }
                 }
             }
@@ -1254,6 +1246,7 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     memset(&ep, 0, sizeof ep);
     ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 4 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
     ep.logits16 = logits16; ep.ld16 = ld16;
+    ep.vec_ok = (logits16 && (reinterpret_cast<uintptr_t>(logits16) & 31) == 0 && (ld16 % 16) == 0) ? 1 : 0;   // 256-bit row-chunk stores
     *n_part_out = 4 * p.sh.n_n;
     CUtensorMap ma, mb;
     int rc = tc_make_maps(c, g, false, p.bn, p.cl, &ma, &mb);

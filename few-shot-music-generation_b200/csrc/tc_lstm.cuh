@@ -484,16 +484,19 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             int stage = 0; uint32_t phase = 0;
             const uint32_t box_bytes = (uint32_t)hr * 128u;
             for (int t = 1; t < p.T; ++t) {
-                const int need = p.ctas_per_group * t;
+                const int need = p.ctas_per_group * 8 * t;   // 8 epilogue warps per half and CTA publish h_{t-1}
                 for (int hs_ = 0; hs_ < 2; ++hs_) {
                     int* counter = p.counters + 2 * g + hs_;
                     while (ld_acquire(counter) < need) { }
                     if (hs_ == 0) FSMG_TR(t, 0);
                     fence_proxy_async_all();
                     for (int kc = 0; kc < KC; ++kc) {
+                        // K chunks in an order rotated by the CTA's slice index: the C CTAs of a group read the same rows, and in
+                        // lock step they would all hit the same L2 lines at the same moment
+                        const int kcr = (kc + j) % KC;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], box_bytes);
-                        tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kc * 64, group_row0 + hs_ * hr, t - 1, &full_bar[stage]);
+                        tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kcr * 64, group_row0 + hs_ * hr, t - 1, &full_bar[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     if (hs_ == 0) FSMG_TR(t, 1);
@@ -519,7 +522,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                         if (kc == 0 && hs_ == 0) FSMG_TR(t, 2);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
-                        const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
+                        const uint32_t sb = smem_u32(sW + ((kc + j) % KC) * CHUNK_W);   // same rotation as the producer
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_f16(d_buf, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, 1u);
@@ -636,11 +639,12 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     c_stash[u0 / 8][1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
                 }
             }
-            // publish this half: barrier over its 8 warps, then ONE gpu-scope release
+            // publish per WARP (the counter counts warps): no CTA-wide barrier, and the gpu-scope release of lane 0 only has to
+            // drain this warp's own h stores (made visible to it by the warp barrier)
             tc_fence_before();
             if (tracer) FSMG_TR(t, 6);
-            named_bar_sync(1 + hs_, 256);
-            if (us == 0 && quad == 0 && lane == 0) { if (tracer) FSMG_TR(t, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(t, 8); }
+            __syncwarp();
+            if (lane == 0) { if (tracer) FSMG_TR(t, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(t, 8); }
             if (ok) {
                 __half* gout = p.gates + r * p.G4p + ucol;
                 float* cdst = p.c + r * p.H + ucol;
