@@ -705,6 +705,10 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     int* counter = p.counters + g;
     const int crank = (CLS > 1) ? (int)cluster_ctarank() : 0;
     constexpr uint16_t CMASK = (uint16_t)((1u << CLS) - 1u);
+    // K chunks are walked in an order rotated per loader (pair / cluster / CTA): the CTAs of a group read the same rows, and in lock
+    // step they would all hit the same L2 lines at the same moment (measured: the load phase ran at half of the L2 throughput cap)
+    const int n_loaders = p.ctas_per_group / (PAIR ? 2 : CLS);
+    const int rot = (((PAIR ? (j >> 1) : (j / CLS)) * KC) / (n_loaders > 0 ? n_loaders : 1)) % KC;
     constexpr int STG_COLS = 5 * U;             // per row tile: gates (2U words) | c (U) | c_prev (U) | dh_out (U), staged by the epilogue warps
     constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS);
 
@@ -736,16 +740,17 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                 FSMG_TR(s, 0);
                 fence_proxy_async_all();
                 for (int kc = 0; kc < KC; ++kc) {
+                    const int kcr = (kc + rot) % KC;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (PAIR) {
                         if (prank == 0) mbar_expect_tx(&full_bar[stage], 2 * box_bytes);
-                        tma_load_3d_2sm(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
+                        tma_load_3d_2sm(sA + stage * STAGE_BYTES, &map_dg, kcr * 64, row_base, t + 1, &full_bar[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     mbar_expect_tx(&full_bar[stage], box_bytes);
-                    if (CLS == 1) tma_load_3d(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage]);
-                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_dg, kc * 64, row_base, t + 1, &full_bar[stage], CMASK);
+                    if (CLS == 1) tma_load_3d(sA + stage * STAGE_BYTES, &map_dg, kcr * 64, row_base, t + 1, &full_bar[stage]);
+                    else if (kc % CLS == crank) tma_load_3d_mc(sA + stage * STAGE_BYTES, &map_dg, kcr * 64, row_base, t + 1, &full_bar[stage], CMASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 FSMG_TR(s, 1);
@@ -767,7 +772,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     if (kc == 0) FSMG_TR(s, 2);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
-                    const uint32_t sb = smem_u32(sW + kc * CHUNK_W);
+                    const uint32_t sb = smem_u32(sW + ((kc + rot) % KC) * CHUNK_W);   // same rotation as the producer
                     if (PAIR) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
