@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
 
 
 def synthetic_batches(w: dict, n_batches: int, seed: int):
-    from oracle import lstm_oracle as O  # synthetic-input generator only (shared with the tests)
+    from data import synthetic as O  # package-side generator: the product arm never imports oracle/
     rng = np.random.RandomState(seed)
     out = []
     for _ in range(n_batches):

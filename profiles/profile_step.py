@@ -19,7 +19,7 @@ n = bench.SEQS_PER_EPISODE * w["episodes"]
 eng = Engine(cfg, max_seqs=n, device="cuda:0")
 eng.init_params(1234)
 rng = np.random.RandomState(0)
-from oracle import lstm_oracle as O  # synthetic inputs only  # noqa: E402
+from data import synthetic as O  # noqa: E402
 
 tok = torch.from_numpy(O.synthetic_tokens(rng, (n, w["max_len"]), w["input_size"], "zipf")).cuda()
 for _ in range(steps):

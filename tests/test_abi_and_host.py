@@ -210,3 +210,14 @@ def test_data_parallel_protocol_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "DP_OK" in outs[0]
+
+
+def test_package_synthetic_generator_matches_oracle_generator():
+    """bench.py's product arm draws its episodes from data.synthetic (no oracle import); the tests draw theirs
+    from the oracle.  Same seed -> same episodes, so parity runs and bench runs see identical inputs."""
+    from data import synthetic as S
+    from oracle import lstm_oracle as O
+    for kind, vocab in (("zipf", 10000), ("uniform", 4708)):
+        a = S.synthetic_episode(np.random.RandomState(5), 5, 5, 4, 32, vocab, kind)
+        b = O.synthetic_episode(np.random.RandomState(5), 5, 5, 4, 32, vocab, kind)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
