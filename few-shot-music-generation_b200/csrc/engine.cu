@@ -103,6 +103,7 @@ struct fsmg_handle {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_dh[2] = {nullptr, nullptr}, ev_dws[2] = {nullptr, nullptr};
     int overlap = 1;
+    int strip_overlap = 0;   // background softmax-gradient pass beside the dH / dWs GEMMs (FSMG_STRIP_OVERLAP=1; measured slower)
     int samp_max = 0;
     // pinned host staging
     int32_t* h_tok = nullptr;
@@ -179,11 +180,24 @@ static void carve(fsmg_handle* h, char* base) {
     const char* env_mb = getenv("FSMG_CHUNK_MB");
     const char* env_ov = getenv("FSMG_OVERLAP");
     const char* env_gr = getenv("FSMG_GRAPH");
+    const char* env_so = getenv("FSMG_STRIP_OVERLAP");
+    h->strip_overlap = env_so ? atoi(env_so) : 0;   // measured: 14.17 ms (1 background CTA/SM: 1.2 TB/s) / 12.65 (6/SM) vs 12.47 serial
     h->use_graph = env_gr ? atoi(env_gr) : 1;
     h->overlap = env_ov ? atoi(env_ov) : 0;   // measured: with 256 MB chunks and stream-K balanced GEMMs, overlapping streams lose (16.97 vs 14.35 ms)
-    const int64_t chunk_mb = env_mb ? atoi(env_mb) : 256;   // measured optimum (sweep 32..768 MB): launch efficiency beats L2 residency
-    int64_t rows = (chunk_mb << 20) / ((int64_t)h->Vp * 2);
-    rows = rows / 128 * 128;
+    // Chunk rows: the dH GEMM of a chunk has ONE 512-wide N tile, so its tile count is rows/256 (cta_group::2 pair tiles).  Pick the
+    // number of chunks so that a chunk is at most one full wave of pair tiles (74 on 148 SMs) and divide the tokens EVENLY: no ragged
+    // last chunk, no stream-K partial sums in dH (measured at cfg 2: 14 chunks of 13 312 rows 12.47 ms -> 10 chunks of 18 432 rows
+    // 12.04 ms, dH 1.85 -> 1.40 ms).  FSMG_CHUNK_MB caps the fp16 logits chunk (default 1 GB); FSMG_CHUNK_ROWS overrides.
+    int n_sm = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+    const int64_t wave_rows = (int64_t)(n_sm / 2) * 256;
+    const int64_t n_chunks = NT > 0 ? cdiv(NT, wave_rows) : 1;
+    int64_t rows = round_up(cdiv(NT, n_chunks), 256);
+    const int64_t chunk_mb = env_mb ? atoi(env_mb) : 1024;
+    const int64_t cap_rows = ((chunk_mb << 20) / ((int64_t)h->Vp * 2)) / 128 * 128;
+    if (rows > cap_rows) rows = cap_rows;
+    const char* env_cr = getenv("FSMG_CHUNK_ROWS");   // explicit row count (tile-count experiments)
+    if (env_cr && atoll(env_cr) > 0) rows = atoll(env_cr);
     if (rows < 128) rows = 128;
     if (rows > NT) rows = round_up(NT, 128);
     h->chunk_rows = (int)rows;
@@ -329,6 +343,53 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
     if (train) FSMG_CUDA_OK(cudaMemsetAsync(h->dws_acc, 0, sizeof(float) * (size_t)H * h->Vp, s));
     // overlap is switched off while profiling so that per-phase event brackets do not double count
     const bool overlap = train && use_tc && h->overlap && !h->prof.on && h->aux[0] != nullptr;
+    // Optional training schedule (FSMG_STRIP_OVERLAP=1) on the tcgen05 route: the HBM-bound softmax-gradient pass of chunk i runs as a background kernel
+    // on a side stream, sharing the SMs with the tensor-bound dH / dWs GEMMs of chunk i-1 (main stream, after the logits GEMM of
+    // chunk i); dlogits is double-buffered.  Per-phase profiling uses the serial schedule below (brackets would overlap).
+    const int64_t n_chunks = cdiv(NT, (int64_t)h->chunk_rows);
+    if (train && use_tc && !overlap && h->strip_overlap && !h->prof.on && h->aux[0] != nullptr && n_chunks >= 2) {
+        cudaStream_t sx = h->aux[0];
+        // dH is zeroed once for the whole step and every chunk's GEMM adds into it (stream-K partials are combined with REDs
+        // anyway): no memset node between the GEMMs while the background pass is resident
+        FSMG_CUDA_OK(cudaMemsetAsync(h->dact[0], 0, sizeof(float) * (size_t)NT * H, s));
+        for (int64_t i = 0; i <= n_chunks; ++i) {
+            int rc;
+            if (i < n_chunks) {
+                const int64_t r0 = i * h->chunk_rows;
+                const int mc = (int)((NT - r0 < h->chunk_rows) ? NT - r0 : h->chunk_rows);
+                const int buf = (int)(i & 1);
+                int n_part = 0;
+                // buffer `buf` was last read by the dH / dWs GEMMs of chunk i-2, already enqueued on s
+                rc = tc_projection_gemm(h->tc, hs + r0 * h->Hp, h->Hp, h->WsT16, h->Hp, sb, h->y_ids, r0, mc, H, h->V1, h->dlogits_b[buf],
+                                        h->Vp, &n_part, s);
+                if (rc) return rc;
+                rc = tc_projection_combine(h->tc, n_part, r0, mc, N, T, h->lse, nll_out, s, /*reset_sched=*/true);
+                if (rc) return rc;
+                FSMG_CUDA_OK(cudaEventRecord(h->ev_ready[buf], s));
+                FSMG_CUDA_OK(cudaStreamWaitEvent(sx, h->ev_ready[buf], 0));
+                rc = tc_projection_strip_bg(h->tc, h->y_ids, r0, mc, h->V1, h->dlogits_b[buf], h->Vp, h->lse, loss_scale, g_sb, sx);
+                if (rc) return rc;
+                FSMG_CUDA_OK(cudaEventRecord(h->ev_dh[buf], sx));
+                h->launches += 3;
+            }
+            if (i >= 1) {
+                const int64_t j = i - 1, r0 = j * h->chunk_rows;
+                const int mc = (int)((NT - r0 < h->chunk_rows) ? NT - r0 : h->chunk_rows);
+                const int buf = (int)(j & 1);
+                FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dh[buf], 0));     // dlogits of chunk j are final
+                rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits_b[buf], h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H, 1.0f, nullptr, 0, 0, 1), false, false, s);
+                if (rc) return rc;
+                rc = gemm_f16(h, mk(H, h->V1, mc, hs + r0 * h->Hp, h->Hp, h->dlogits_b[buf], h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 0, 1),
+                              true, true, s);
+                if (rc) return rc;
+            }
+        }
+        int64_t total = (int64_t)H * h->V1;
+        unpad_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(h->dws_acc, h->Vp, g_sw, h->V1, H, h->V1);
+        LAUNCH_COUNT(h);
+        FSMG_LAUNCH_OK();
+        return FSMG_OK;
+    }
     int64_t chunk_idx = 0;
     for (int64_t r0 = 0; r0 < NT; r0 += h->chunk_rows, ++chunk_idx) {
         int mc = (int)((NT - r0 < h->chunk_rows) ? NT - r0 : h->chunk_rows);
@@ -355,7 +416,7 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
                 rc = tc_projection_post(h->tc, n_part, h->y_ids, r0, mc, N, T, h->V1, train ? h->dlogits : nullptr, h->Vp, h->lse,
                                         nll_out, loss_scale, g_sb, s);
             }
-            h->launches += 2;
+            h->launches += train ? 3 : 2;
             if (rc) return rc;
         } else {
             ProfScope ps(h, PH_PROJ_FWD, s);
@@ -942,6 +1003,18 @@ int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const 
     if (rc) return rc;
     if (!tc_gemm_supported(g, a_mn_major != 0, b_mn_major != 0)) return set_error(FSMG_ERR_INVALID, "shape unsupported by the tcgen05 GEMM");
     return tc_gemm(ctx, g, a_mn_major != 0, b_mn_major != 0, s);
+}
+
+// one in-place softmax-gradient pass (dlogits = exp(logit - lse) - onehot(y), db += alpha * column sums) over a caller-provided
+// fp16 logits block, in an explicit kernel variant: parity test of the pass on its own + micro-benchmark of the variants
+int fsmg_debug_softmax_grad(int32_t rows, int32_t vocab1, int64_t ld, void* d_logits_f16, const float* d_lse, const int32_t* d_y,
+                            float alpha, float* d_db, int32_t mode, int32_t param, int32_t waves, void* stream) {
+    if (rows <= 0 || vocab1 <= 0 || ld < vocab1 || (ld % 8) != 0 || !d_logits_f16 || !d_lse || !d_y || !d_db)
+        return set_error(FSMG_ERR_INVALID, "fsmg_debug_softmax_grad: bad argument");
+    int dev = 0, sms = 148;
+    FSMG_CUDA_OK(cudaGetDevice(&dev));
+    FSMG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    return tc_softmax_grad_launch(sms, mode, param, waves, d_y, 0, rows, vocab1, (__half*)d_logits_f16, ld, d_lse, alpha, d_db, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -779,21 +779,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 }
 
 // combine the per-(row, n-tile) (max, sumexp) partials: lse = M + log(sum_i s_i * exp(m_i - M)); nll = lse - tgt
-__global__ void lse_combine_kernel(const float2* __restrict__ part, int n_tiles, const float* __restrict__ tgt,
-                                   int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
-                                   float* __restrict__ nll_out) {
-    int lr = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) lse_combine_kernel(const float2* __restrict__ part, int n_tiles, const float* __restrict__ tgt,
+                                                          int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
+                                                          float* __restrict__ nll_out, int* __restrict__ sched) {
+    // (also resets the strip scheduler of the background softmax-grad pass that follows: no memset node on the side stream)
+    if (sched != nullptr && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < 1032; i += blockDim.x) sched[i] = 0;
+    // one warp per row: the row's partials are contiguous (n_tiles x 8 B), so every load instruction is one coalesced line
+    // (one thread per row walked 2.5 KB-strided addresses: 27 us per 13 k-row chunk, 0.37 ms per step)
+    const int lr = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (lr >= rows) return;
     const float2* p = part + (int64_t)lr * n_tiles;
     float m = -INFINITY;
-    for (int i = 0; i < n_tiles; ++i) m = fmaxf(m, p[i].x);
+    for (int i = lane; i < n_tiles; i += 32) m = fmaxf(m, __ldcg(&p[i]).x);
+    m = warp_max(m);
     float s = 0.0f;
-    for (int i = 0; i < n_tiles; ++i) s += p[i].y * expf(p[i].x - m);
-    float lse = m + logf(s);
-    int64_t r = row0 + lr;
-    if (lse_out) lse_out[r] = lse;
-    int t = (int)(r / N), n = (int)(r % N);
-    if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[lr];
+    for (int i = lane; i < n_tiles; i += 32) { const float2 v = __ldcg(&p[i]); s += v.y * expf(v.x - m); }
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float lse = m + logf(s);
+        const int64_t r = row0 + lr;
+        if (lse_out) lse_out[r] = lse;
+        const int t = (int)(r / N), n = (int)(r % N);
+        if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[lr];
+    }
 }
 
 // in place over the fp16 logits chunk: dlogits = exp(logit - lse) - onehot(y)   (unscaled)
@@ -906,22 +916,19 @@ __global__ void __launch_bounds__(THREADS) softmax_grad_fused_kernel(__half* __r
 
 // Strip version of the fused post-pass (default): a CTA of 128 threads owns a strip of ROWS rows x 1024 columns; each
 // thread owns 8 fixed columns and walks down the strip with 8 rows of 16-byte loads in flight, so column sums stay
-// in 8 registers and the kernel needs ~50 registers and 256 B of smem: it can share an SM with a GEMM CTA, and
-// there are enough small CTAs (cols/1024 x rows/ROWS) to keep >80 KB per SM in flight.
+// in 8 registers and the kernel needs <= 80 registers and 256 B of smem: it can share an SM with a GEMM CTA.
 template <int ROWS>
-__global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
-                                                                 const float* __restrict__ lse_all, const int32_t* __restrict__ y,
-                                                                 int64_t row0, int rows, float alpha, float* __restrict__ db) {
-    __shared__ float s_lse[ROWS];
-    __shared__ int s_tgt[ROWS];
-    const int r_begin = blockIdx.y * ROWS;
+__device__ __forceinline__ void softmax_grad_strip_item(__half* __restrict__ logits, int64_t ld, int vp1, const float* __restrict__ lse_all,
+                                                        const int32_t* __restrict__ y, int64_t row0, int rows, float alpha,
+                                                        float* __restrict__ db, int bx, int by, float* s_lse, int* s_tgt) {
+    const int r_begin = by * ROWS;
     const int n_rows = min(ROWS, rows - r_begin);
     if (threadIdx.x < n_rows) {   // the row-wise log-sum-exp was combined by lse_combine_kernel just before
         s_lse[threadIdx.x] = lse_all[row0 + r_begin + threadIdx.x];
         s_tgt[threadIdx.x] = y[row0 + r_begin + threadIdx.x];
     }
     __syncthreads();
-    const int v0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    const int v0 = (bx * 128 + threadIdx.x) * 8;
     if (v0 >= ld) return;
     float csum[8];
 #pragma unroll
@@ -971,6 +978,143 @@ __global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restr
         if (v0 + e < vp1) atomicAdd(db + v0 + e, alpha * csum[e]);
 }
 
+template <int ROWS>
+__global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
+                                                                    const float* __restrict__ lse_all, const int32_t* __restrict__ y,
+                                                                    int64_t row0, int rows, float alpha, float* __restrict__ db) {
+    __shared__ float s_lse[ROWS];
+    __shared__ int s_tgt[ROWS];
+    softmax_grad_strip_item<ROWS>(logits, ld, vp1, lse_all, y, row0, rows, alpha, db, blockIdx.x, blockIdx.y, s_lse, s_tgt);
+}
+
+// Streaming flavour (default): ONE wave of CTAs (6 per SM x 128 threads); CTA (bx, by) owns 1024 columns x one long row segment and
+// walks down it software-pipelined — batch b+1 (4 rows of 16-byte loads per thread, plus the rows' lse / target) is in flight while
+// batch b is exponentiated and stored, so every thread always has loads outstanding; no shared memory, no barriers.  All CTAs are
+// co-resident and own equal work, so there is no partial last wave (the strip grids lost up to 20 % to it).
+template <int RB>
+__global__ void __launch_bounds__(128, 6) softmax_grad_stream_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
+                                                                     const float* __restrict__ lse_all, const int32_t* __restrict__ y,
+                                                                     int64_t row0, int rows, int seg_rows, float alpha,
+                                                                     float* __restrict__ db) {
+    const int v0 = (blockIdx.x * 128 + threadIdx.x) * 8;
+    if (v0 >= ld) return;
+    const int r_begin = blockIdx.y * seg_rows;
+    const int r_end = min(rows, r_begin + seg_rows);
+    if (r_begin >= r_end) return;
+    __half* base = logits + (int64_t)r_begin * ld + v0;
+    const float* lse_p = lse_all + row0 + r_begin;
+    const int32_t* y_p = y + row0 + r_begin;
+    const int n = r_end - r_begin;
+    const bool interior = v0 + 8 <= vp1;
+    float csum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) csum[e] = 0.0f;
+    uint4 buf[2][RB];
+    float nl2[2][RB];
+    int tgc[2][RB];
+    auto load = [&](int slot, int r) {
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+            if (r + b < n) {
+                buf[slot][b] = __ldcg(reinterpret_cast<const uint4*>(base + (int64_t)(r + b) * ld));
+                nl2[slot][b] = -__ldg(lse_p + r + b) * 1.4426950408889634f;
+                tgc[slot][b] = __ldg(y_p + r + b) - v0;
+            }
+    };
+    auto process = [&](int slot, int r) {
+#pragma unroll
+        for (int b = 0; b < RB; ++b)
+            if (r + b < n) {
+                __half2* h2 = reinterpret_cast<__half2*>(&buf[slot][b]);
+                const float l2 = nl2[slot][b];
+                const int tg = tgc[slot][b];
+                if (interior && (unsigned)tg >= 8u) {      // fast path: no column guards, no target in these 8 columns
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(h2[q]);
+                        const float a = fast_ex2(fmaf(f.x, 1.4426950408889634f, l2));
+                        const float bb = fast_ex2(fmaf(f.y, 1.4426950408889634f, l2));
+                        h2[q] = __floats2half2_rn(a, bb);
+                        csum[2 * q] += a;
+                        csum[2 * q + 1] += bb;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 f = __half22float2(h2[q]);
+                        const int v = v0 + 2 * q;
+                        const float a = v < vp1 ? fast_ex2(fmaf(f.x, 1.4426950408889634f, l2)) - (2 * q == tg ? 1.0f : 0.0f) : 0.0f;
+                        const float bb = v + 1 < vp1 ? fast_ex2(fmaf(f.y, 1.4426950408889634f, l2)) - (2 * q + 1 == tg ? 1.0f : 0.0f) : 0.0f;
+                        h2[q] = __floats2half2_rn(a, bb);
+                        csum[2 * q] += a;
+                        csum[2 * q + 1] += bb;
+                    }
+                }
+                *reinterpret_cast<uint4*>(base + (int64_t)(r + b) * ld) = buf[slot][b];
+            }
+    };
+    load(0, 0);
+    for (int r = 0; r < n; r += 2 * RB) {
+        load(1, r + RB);
+        process(0, r);
+        load(0, r + 2 * RB);
+        process(1, r + RB);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (v0 + e < vp1) atomicAdd(db + v0 + e, alpha * csum[e]);
+}
+
+// Persistent flavour (default): 6 CTAs per SM walk the strips with a static stride (column block fastest, so the CTAs running at
+// any moment cover the same rows: DRAM-page friendly).  The plain grid's last partial wave of CTAs ran at a fraction of the
+// occupancy (measured with 18 432-row chunks: 64-row strips = 3.24 waves 1.94 ms, 32-row strips = 6.49 waves 1.59 ms per step).
+template <int ROWS>
+__global__ void __launch_bounds__(128, 6) softmax_grad_strip_loop_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
+                                                                         const float* __restrict__ lse_all, const int32_t* __restrict__ y,
+                                                                         int64_t row0, int rows, float alpha, float* __restrict__ db) {
+    __shared__ float s_lse[ROWS];
+    __shared__ int s_tgt[ROWS];
+    const int n_bx = (int)((ld + 1023) / 1024);
+    const int n_items = n_bx * ((rows + ROWS - 1) / ROWS);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        __syncthreads();                                   // previous strip done with s_lse / s_tgt
+        softmax_grad_strip_item<ROWS>(logits, ld, vp1, lse_all, y, row0, rows, alpha, db, item % n_bx, item / n_bx, s_lse, s_tgt);
+    }
+}
+
+// Same pass as a BACKGROUND kernel that shares the SMs with a persistent GEMM (the dH / dWs GEMMs of the previous chunk run
+// on the caller's stream meanwhile): the GEMM CTA leaves 10 240 registers and ~1.5 KB of shared memory per SM — room for
+// exactly one of these CTAs (128 threads x 80 registers, 256 B).  Strips are handed out by a global counter, and at most
+// `max_per_sm` CTAs stay alive per SM (claimed through %smid; the others exit at once), so that however the block scheduler
+// spreads the grid, a GEMM CTA arriving later always finds its registers free.
+//   sched[0] = next strip, sched[1 + smid] = CTAs that claimed SM smid   (zeroed by the host before the launch)
+template <int ROWS>
+__global__ void __launch_bounds__(128, 6) softmax_grad_strip_bg_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
+                                                                       const float* __restrict__ lse_all, const int32_t* __restrict__ y,
+                                                                       int64_t row0, int rows, float alpha, float* __restrict__ db,
+                                                                       int* __restrict__ sched, int max_per_sm) {
+    __shared__ float s_lse[ROWS];
+    __shared__ int s_tgt[ROWS];
+    __shared__ int s_item;
+    const int n_bx = (int)((ld + 1023) / 1024);
+    const int n_items = n_bx * ((rows + ROWS - 1) / ROWS);
+    if (threadIdx.x == 0) {
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        s_item = atomicAdd(&sched[1 + (smid & 1023)], 1) < max_per_sm ? 0 : -1;
+    }
+    __syncthreads();
+    if (s_item < 0) return;
+    for (;;) {
+        __syncthreads();                                   // previous strip done with s_lse / s_tgt / s_item
+        if (threadIdx.x == 0) s_item = atomicAdd(&sched[0], 1);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= n_items) break;
+        softmax_grad_strip_item<ROWS>(logits, ld, vp1, lse_all, y, row0, rows, alpha, db, item % n_bx, item / n_bx, s_lse, s_tgt);
+    }
+}
+
 }  // namespace tc
 
 // =====================================================================================================
@@ -979,6 +1123,8 @@ __global__ void __launch_bounds__(128) softmax_grad_strip_kernel(__half* __restr
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+constexpr int STRIP_ROWS = 32;    // rows per strip of the background softmax-grad kernel
 
 struct TcContext {
     bool ready = false;
@@ -989,6 +1135,9 @@ struct TcContext {
     float* tgt = nullptr;
     int part_tiles = 0;
     int* counters = nullptr;   // [256] group-progress counters of the persistent recurrent kernels
+    int* strip_sched = nullptr;
+    int strip_per_sm = 1;      // live background softmax-grad CTAs per SM (FSMG_STRIP_PER_SM)
+    int strip_mode = 2, strip_param = 2, strip_waves = 6;   // softmax-grad pass variant (FSMG_STRIP=mode,param,waves; see tc_softmax_grad_launch)
     long long* trace = nullptr; // [128] debug timeline (FSMG_TRACE=1)
     int enabled = 1;
     int cluster = 2;           // CTAs per cluster of the GEMM core (2 = cta_group::2 pairs, 1 = single-SM MMAs)
@@ -999,6 +1148,7 @@ struct TcContext {
     int lstm_cluster = 1;      // CTAs per cluster of the persistent recurrent kernels (1, 2 or 4: operand multicast)
     int lstm_split = 1;        // forward recurrent kernel: two interleaved half-groups per CTA (FSMG_LSTM_SPLIT=0: one lock-step group)
     int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
+    int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
 };
 
@@ -1008,6 +1158,7 @@ static inline void tc_carve(TcContext& c, B& b, int /*Nmax*/, int /*T*/, int V1,
     c.part = b.template take<float2>((int64_t)chunk_rows * c.part_tiles);
     c.tgt = b.template take<float>(chunk_rows);
     c.counters = b.template take<int>(256);
+    c.strip_sched = b.template take<int>(1032);   // [0] next strip, [1 + smid] claims (background softmax-grad pass)
     c.trace = b.template take<long long>(128);
 }
 
@@ -1027,6 +1178,12 @@ static inline int tc_init(TcContext& c) {
     c.streamk = envs ? atoi(envs) : 1;
     const char* envp = getenv("FSMG_LSTM_PAIR");
     c.lstm_pair = envp ? atoi(envp) : 1;   // bit 0: backward (measured 2.64 -> 1.99 ms), bit 1: forward (neutral)
+    const char* envr = getenv("FSMG_LSTM_ROT");
+    if (envr) c.lstm_rot = atoi(envr);
+    const char* envst = getenv("FSMG_STRIP");
+    if (envst) sscanf(envst, "%d,%d,%d", &c.strip_mode, &c.strip_param, &c.strip_waves);
+    const char* envps = getenv("FSMG_STRIP_PER_SM");
+    if (envps && atoi(envps) > 0) c.strip_per_sm = atoi(envps);
     const char* envsp = getenv("FSMG_LSTM_SPLIT");
     c.lstm_split = envsp ? atoi(envsp) : 1;
     const char* envl = getenv("FSMG_LSTM_CLUSTER");
@@ -1056,6 +1213,11 @@ static inline int tc_init(TcContext& c) {
     FSMG_SET_SMEM(128, tc::EPI_SCATTER, false, false);
     FSMG_SET_SMEM(128, tc::EPI_LSE, false, false);
 #undef FSMG_SET_SMEM
+    // the small kernels that run between / beside the persistent GEMMs of the projection ask for the same (maximum) shared-memory
+    // carve-out as the GEMMs: an SM whose carve-out had been shrunk for them would have to drain before a GEMM CTA could land on it
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::lse_combine_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::softmax_grad_strip_bg_kernel<STRIP_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::softmax_grad_strip_kernel<STRIP_ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     c.ready = true;
     return 0;
 }
@@ -1274,19 +1436,75 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
 }
 
 // LSE combine (+ in-place softmax gradient and bias gradient when training) over the chunk
+static inline int tc_projection_combine(TcContext& c, int n_part, int64_t row0, int mc, int N, int T, float* lse, float* nll_out,
+                                        cudaStream_t s, bool reset_sched = false) {
+    tc::lse_combine_kernel<<<cdiv(mc, 8), 256, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out,
+                                                       reset_sched ? c.strip_sched : nullptr);
+    FSMG_LAUNCH_OK();
+    return 0;
+}
+
+// mode 0: strip grid (param = rows per strip: 16 / 32 / 64 / 96 / 128);  mode 1: persistent strip loop (param = 8 / 16 / 32 rows);
+// mode 2: streaming, one co-resident wave of `waves` CTAs per SM (param = rows per batch: 1 / 2 / 4)
+static inline int tc_softmax_grad_launch(int num_sms, int mode, int param, int waves, const int32_t* y, int64_t row0, int mc, int V1,
+                                         __half* logits16, int64_t ld16, const float* lse, float db_alpha, float* db, cudaStream_t s) {
+#define FSMG_STRIP_GO(R)                                                                                                         \
+    do {                                                                                                                         \
+        dim3 grid(cdiv(ld16, 1024), cdiv(mc, R));                                                                                \
+        tc::softmax_grad_strip_kernel<R><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);               \
+    } while (0)
+    if (waves < 1 || waves > 6) waves = 6;
+    if (mode == 2) {
+        const int n_bx = cdiv(ld16, 1024);
+        int segs = (waves * num_sms) / n_bx;                  // one co-resident wave
+        if (segs < 1) segs = 1;
+        int seg_rows = cdiv(mc, segs);
+        if (seg_rows < 8) seg_rows = 8;
+        dim3 grid(n_bx, cdiv(mc, seg_rows));
+        if (param == 1) tc::softmax_grad_stream_kernel<1><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, seg_rows, db_alpha, db);
+        else if (param == 4) tc::softmax_grad_stream_kernel<4><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, seg_rows, db_alpha, db);
+        else tc::softmax_grad_stream_kernel<2><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, seg_rows, db_alpha, db);
+    } else if (mode == 1) {
+        const int grid = waves * num_sms;
+        if (param == 8) tc::softmax_grad_strip_loop_kernel<8><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
+        else if (param == 16) tc::softmax_grad_strip_loop_kernel<16><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
+        else tc::softmax_grad_strip_loop_kernel<32><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
+    } else if (param == 16) FSMG_STRIP_GO(16);
+    else if (param == 64) FSMG_STRIP_GO(64);
+    else if (param == 96) FSMG_STRIP_GO(96);
+    else if (param == 128) FSMG_STRIP_GO(128);
+    else FSMG_STRIP_GO(32);
+#undef FSMG_STRIP_GO
+    FSMG_LAUNCH_OK();
+    return 0;
+}
+
+static inline int tc_projection_strip(TcContext& c, const int32_t* y, int64_t row0, int mc, int V1, __half* logits16, int64_t ld16,
+                                      const float* lse, float db_alpha, float* db, cudaStream_t s) {
+    return tc_softmax_grad_launch(c.num_sms, c.strip_mode, c.strip_param, c.strip_waves, y, row0, mc, V1, logits16, ld16, lse, db_alpha, db, s);
+}
+
+// background flavour: launched on a side stream while persistent GEMMs own the SMs (see softmax_grad_strip_bg_kernel)
+static inline int tc_projection_strip_bg(TcContext& c, const int32_t* y, int64_t row0, int mc, int V1, __half* logits16, int64_t ld16,
+                                         const float* lse, float db_alpha, float* db, cudaStream_t s) {
+    // (c.strip_sched was zeroed by the chunk's lse_combine_kernel)
+    // up to 6 CTAs fit an otherwise empty SM: with 6 x num_sms CTAs every SM sees at least one candidate whichever way the
+    // scheduler packs them; the surplus exits on its first instruction (claim refused or no strips left)
+    const int items = cdiv(ld16, 1024) * cdiv(mc, STRIP_ROWS);
+    int grid = 6 * c.num_sms;
+    if (grid > items) grid = items;
+    tc::softmax_grad_strip_bg_kernel<STRIP_ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db, c.strip_sched,
+                                                                      c.strip_per_sm);
+    FSMG_LAUNCH_OK();
+    return 0;
+}
+
 static inline int tc_projection_post(TcContext& c, int n_part, const int32_t* y, int64_t row0, int mc, int N, int T, int V1,
                                      __half* logits16, int64_t ld16, float* lse, float* nll_out, float db_alpha, float* db,
                                      cudaStream_t s) {
-    if (!logits16) {
-        tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
-    } else {
-        constexpr int ROWS = 32;    // rows per strip (measured: 32 -> 1.87 ms, 128 -> 2.45 ms per step: more, smaller CTAs stream better)
-        tc::lse_combine_kernel<<<cdiv(mc, 128), 128, 0, s>>>(c.part, n_part, c.tgt, row0, mc, N, T, lse, nll_out);
-        dim3 grid(cdiv(ld16, 1024), cdiv(mc, ROWS));
-        tc::softmax_grad_strip_kernel<ROWS><<<grid, 128, 0, s>>>(logits16, ld16, V1, lse, y, row0, mc, db_alpha, db);
-    }
-    FSMG_LAUNCH_OK();
-    return 0;
+    int rc = tc_projection_combine(c, n_part, row0, mc, N, T, lse, nll_out, s);
+    if (rc || !logits16) return rc;
+    return tc_projection_strip(c, y, row0, mc, V1, logits16, ld16, lse, db_alpha, db, s);
 }
 
 }  // namespace fsmg

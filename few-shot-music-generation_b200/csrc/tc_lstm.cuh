@@ -124,6 +124,7 @@ struct LstmParams {
     int stage_bytes, stages;   // TMA ring geometry (host-computed: stages sized to the rows actually exchanged)
     int row_offset;        // first sequence handled by this launch (batch slicing when N is large)
     int n_rows;            // sequences handled by this launch
+    int rotate;            // walk the K chunks in an order rotated per loader (FSMG_LSTM_ROT bit 0: backward, bit 1: forward)
 };
 
 __host__ __device__ constexpr int lstm_threads(int mt) { return 64 + 128 * mt; }   // producer warp, MMA warp, 4 epilogue warps per row tile
@@ -493,7 +494,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     for (int kc = 0; kc < KC; ++kc) {
                         // K chunks in an order rotated by the CTA's slice index: the C CTAs of a group read the same rows, and in
                         // lock step they would all hit the same L2 lines at the same moment
-                        const int kcr = (kc + j) % KC;
+                        const int kcr = (kc + (p.rotate ? j : 0)) % KC;
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], box_bytes);
                         tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kcr * 64, group_row0 + hs_ * hr, t - 1, &full_bar[stage]);
@@ -522,7 +523,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                         if (kc == 0 && hs_ == 0) FSMG_TR(t, 2);
                         tc_fence_after();
                         const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
-                        const uint32_t sb = smem_u32(sW + ((kc + j) % KC) * CHUNK_W);   // same rotation as the producer
+                        const uint32_t sb = smem_u32(sW + ((kc + (p.rotate ? j : 0)) % KC) * CHUNK_W);   // same rotation as the producer
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             umma_f16(d_buf, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, 1u);
@@ -708,7 +709,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     // K chunks are walked in an order rotated per loader (pair / cluster / CTA): the CTAs of a group read the same rows, and in lock
     // step they would all hit the same L2 lines at the same moment (measured: the load phase ran at half of the L2 throughput cap)
     const int n_loaders = p.ctas_per_group / (PAIR ? 2 : CLS);
-    const int rot = (((PAIR ? (j >> 1) : (j / CLS)) * KC) / (n_loaders > 0 ? n_loaders : 1)) % KC;
+    const int rot = p.rotate ? (((PAIR ? (j >> 1) : (j / CLS)) * KC) / (n_loaders > 0 ? n_loaders : 1)) % KC : 0;
     constexpr int STG_COLS = 5 * U;             // per row tile: gates (2U words) | c (U) | c_prev (U) | dh_out (U), staged by the epilogue warps
     constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS);
 
@@ -1031,7 +1032,11 @@ static inline int lstm_launch(K kernel, int grid, int threads, int cls, int smem
     cfg.stream = s;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they wait on each other's counters
-    attr[0].val.cooperative = 1;
+    // FSMG_COOP=0 drops the attribute (profiling only: ncu cannot replay a cooperative launch that also carries a cluster
+    // dimension — the launch list stopped at the pair-mode backward kernel; the grid never exceeds the SM count, so with the
+    // stream otherwise idle every CTA is resident anyway)
+    static const int coop = [] { const char* e = getenv("FSMG_COOP"); return e ? atoi(e) : 1; }();
+    attr[0].val.cooperative = coop ? 1 : 0;
     attr[1].id = cudaLaunchAttributeClusterDimension;
     attr[1].val.clusterDim.x = cls; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
@@ -1111,7 +1116,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
         FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
         tc::LstmParams p;
         memset(&p, 0, sizeof p);
-        p.pre = pre; p.gates = gates; p.c = cbuf; p.hs = hs; p.counters = c.counters;
+        p.pre = pre; p.gates = gates; p.c = cbuf; p.hs = hs; p.counters = c.counters; p.rotate = (c.lstm_rot & 2) != 0;
         p.N = N; p.T = T; p.H = H; p.Hp = Hp; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (H / 64) * 4 * pl.U * 128;
@@ -1151,7 +1156,7 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
         tc::LstmParams p;
         memset(&p, 0, sizeof p);
-        p.dh_out = dh_out; p.dgates = dgates; p.gates = const_cast<__half*>(gates); p.c = const_cast<float*>(cbuf); p.counters = c.counters;
+        p.dh_out = dh_out; p.dgates = dgates; p.gates = const_cast<__half*>(gates); p.c = const_cast<float*>(cbuf); p.counters = c.counters; p.rotate = (c.lstm_rot & 1) != 0;
         p.N = N; p.T = T; p.H = H; p.Hp = 0; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (4 * H / 64) * pl.U * 128;

@@ -152,6 +152,14 @@ int64_t fsmg_last_launch_count(const fsmg_handle* h);
 int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const void* d_b_f16,
                     float* d_c, int32_t a_mn_major, int32_t b_mn_major, int32_t use_simt, void* stream);
 
+/* One in-place softmax-gradient pass over an fp16 logits block [rows, ld] (K7/K8 of the hot path, reference
+ * lstm_baseline.py:70-75 + tf.gradients through sequence_loss): logits[r, v] <- exp(logits[r, v] - lse[r]) - (v == y[r]),
+ * db[v] += alpha * sum_r of that, for v < vocab1 (columns vocab1..ld-1 are zeroed).  mode/param/waves select the kernel
+ * variant (0 = strip grid, 1 = persistent strips, 2 = streaming; see csrc/tc_gemm.cuh): test + micro-benchmark hook. */
+int fsmg_debug_softmax_grad(int32_t rows, int32_t vocab1, int64_t ld, void* d_logits_f16, const float* d_lse,
+                            const int32_t* d_y, float alpha, float* d_db, int32_t mode, int32_t param, int32_t waves,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

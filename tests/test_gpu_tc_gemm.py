@@ -58,3 +58,32 @@ def test_simt_gemm_matches_too(lib):
     for mn in (False, True):
         c, ref = run_gemm(lib, torch, 200, 304, 136, mn, simt=1)
         assert (c - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [(0, 32, 6), (0, 128, 6), (1, 8, 6), (1, 32, 6), (2, 1, 6), (2, 2, 6), (2, 4, 3)],
+                         ids=lambda v: "mode%d_p%d_w%d" % v)
+@pytest.mark.parametrize("shape", [(5, 37), (300, 1000), (777, 10001)], ids=lambda s: "%dx%d" % s)
+def test_softmax_grad_pass_matches_torch(lib, variant, shape):
+    """dlogits = softmax(logits) - onehot(y) in place over fp16 logits + bias-gradient column sums (reference
+    lstm_baseline.py:70-75 differentiated): every kernel variant against fp32 torch, ragged sizes included."""
+    import torch
+    from fsmg import _lib
+    rows, v1 = shape
+    ld = (v1 + 15) // 16 * 16
+    g = torch.Generator(device="cuda").manual_seed(rows * 131 + v1)
+    logits = (torch.randn(rows, ld, device="cuda", generator=g) * 3).half()
+    y = torch.randint(0, v1, (rows,), device="cuda", dtype=torch.int32, generator=g)
+    lse = torch.logsumexp(logits[:, :v1].float(), dim=1).contiguous()
+    want = torch.softmax(logits[:, :v1].float(), dim=1)
+    want[torch.arange(rows, device="cuda"), y.long()] -= 1.0
+    db = torch.zeros(v1, device="cuda")
+    work = logits.clone()
+    mode, param, waves = variant
+    _lib.check(lib.fsmg_debug_softmax_grad(rows, v1, ld, work.data_ptr(), lse.data_ptr(), y.data_ptr(), 0.5, db.data_ptr(),
+                                           mode, param, waves, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    got = work[:, :v1].float()
+    assert torch.allclose(got, want, atol=2e-3, rtol=2e-3), float((got - want).abs().max())
+    assert float(work[:, v1:].float().abs().max() if ld > v1 else 0.0) == 0.0       # padding columns are zeroed
+    assert torch.allclose(db, 0.5 * want.sum(0), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-2)
