@@ -91,6 +91,7 @@ class Engine:
         self._tok = torch.empty(self.max_seqs * self.T, dtype=torch.int32, device=dev)
         self._pinned_tok = torch.empty(self.max_seqs * self.T, dtype=torch.int32).pin_memory()
         self._pinned_scal = torch.empty(8, dtype=torch.float32).pin_memory()
+        self._h2d_done: Optional[torch.cuda.Event] = None
 
     # ---- parameters ---------------------------------------------------------------------------
     def param_shapes(self) -> Dict[str, tuple]:
@@ -177,9 +178,14 @@ class Engine:
         n = tok.shape[0]
         if n > self.max_seqs:
             raise FsmgError(f"{n} sequences > engine capacity {self.max_seqs}")
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()      # the previous asynchronous H2D copy has finished reading the pinned buffer
         self._pinned_tok[: n * self.T].copy_(torch.from_numpy(tok.reshape(-1)))
         dev = self._tok[: n * self.T]
         dev.copy_(self._pinned_tok[: n * self.T], non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
         return dev.view(n, self.T)
 
     def train_host(self, tokens: np.ndarray, global_tokens: Optional[int] = None) -> float:
