@@ -94,7 +94,9 @@ struct fsmg_handle {
     float *P0 = nullptr, *s_logits2 = nullptr;
     int* s_step = nullptr;
     bool samp_stale = true;
-    cudaGraphExec_t samp_graph = nullptr;   // one captured decode step (replayed n_tokens times)
+    cudaGraphExec_t samp_graph = nullptr;   // one captured decode step
+    cudaGraphExec_t samp_graph_multi = nullptr;   // 16 consecutive decode steps
+    int64_t samp_step_launches = 0;
     int samp_graph_n = 0;
     int chunk_rows = 0;
     // projection backward overlap: dH / dWs GEMMs of chunk i run on two auxiliary streams while the logits GEMM of
@@ -601,8 +603,7 @@ static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
                         h->params + h->sb_off), false, false, s);
     if (rc) return rc;
     argmax_rows_step_kernel<<<n, 256, 0, s>>>(h->s_logits2, h->Vp, h->V1, h->samp_ids, h->samp_out, 4096, h->s_step);
-    bump_counter_kernel<<<1, 32, 0, s>>>(h->s_step);
-    h->launches += 2;
+    h->launches += 1;
     FSMG_LAUNCH_OK();
     return FSMG_OK;
 }
@@ -614,7 +615,7 @@ static int sample_greedy_split(fsmg_handle* h, int n, int n_tokens, int32_t* d_o
     if (h->samp_stale && (rc = sampler_prepare(h, s))) return rc;
     fill_i32_kernel<<<cdiv(n, TB), TB, 0, s>>>(h->samp_ids, n, h->V);   // word = start word (lstm_baseline.py:138)
     LAUNCH_COUNT(h);
-    FSMG_CUDA_OK(cudaMemsetAsync(h->s_step, 0, sizeof(int), s));
+    FSMG_CUDA_OK(cudaMemsetAsync(h->s_step, 0, 2 * sizeof(int), s));
     for (int l = 0; l < h->L; ++l) {   // zero_state (lstm_baseline.py:140)
         FSMG_CUDA_OK(cudaMemsetAsync(h->s_c[l], 0, sizeof(float) * n * H, s));
         FSMG_CUDA_OK(cudaMemsetAsync(h->h3[l], 0, sizeof(__half) * (size_t)n * 3 * h->Hp, s));
@@ -624,23 +625,33 @@ static int sample_greedy_split(fsmg_handle* h, int n, int n_tokens, int32_t* d_o
     if (use_graph) {
         // the decode step is identical for every token (the step index lives on the device): capture it once on an
         // internal stream and replay the graph — one launch per generated token instead of ~8
+        // two graphs: SAMP_UNROLL consecutive steps (bulk of the sequence: 1/16th of the graph launches and of the
+        // launch-to-launch gaps) and a single step (remainder)
+        static const int SAMP_UNROLL = [] { const char* e = getenv("FSMG_SAMPLE_UNROLL"); int v = e ? atoi(e) : 16; return v < 1 ? 1 : v; }();
         if (!h->samp_graph || h->samp_graph_n != n) {
             if (h->samp_graph) { cudaGraphExecDestroy(h->samp_graph); h->samp_graph = nullptr; }
-            cudaGraph_t graph = nullptr;
-            FSMG_CUDA_OK(cudaStreamBeginCapture(h->aux[0], cudaStreamCaptureModeThreadLocal));
-            int64_t saved = h->launches;
-            rc = sample_step_split(h, n, h->aux[0]);
-            h->launches = saved;
-            cudaError_t ce = cudaStreamEndCapture(h->aux[0], &graph);
-            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-            if (ce != cudaSuccess) return set_error(FSMG_ERR_CUDA, "graph capture of the decode step failed: %s", cudaGetErrorString(ce));
-            ce = cudaGraphInstantiate(&h->samp_graph, graph, 0);
-            cudaGraphDestroy(graph);
-            if (ce != cudaSuccess) return set_error(FSMG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+            if (h->samp_graph_multi) { cudaGraphExecDestroy(h->samp_graph_multi); h->samp_graph_multi = nullptr; }
+            for (int which = 0; which < 2; ++which) {
+                cudaGraph_t graph = nullptr;
+                FSMG_CUDA_OK(cudaStreamBeginCapture(h->aux[0], cudaStreamCaptureModeThreadLocal));
+                int64_t saved = h->launches;
+                rc = 0;
+                for (int k = 0; k < (which ? SAMP_UNROLL : 1) && !rc; ++k) rc = sample_step_split(h, n, h->aux[0]);
+                if (which == 0) h->samp_step_launches = h->launches - saved;
+                h->launches = saved;
+                cudaError_t ce = cudaStreamEndCapture(h->aux[0], &graph);
+                if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return set_error(FSMG_ERR_CUDA, "graph capture of the decode step failed: %s", cudaGetErrorString(ce));
+                ce = cudaGraphInstantiate(which ? &h->samp_graph_multi : &h->samp_graph, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ce != cudaSuccess) return set_error(FSMG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+            }
             h->samp_graph_n = n;
         }
-        for (int step = 0; step < n_tokens; ++step) FSMG_CUDA_OK(cudaGraphLaunch(h->samp_graph, s));
-        h->launches += n_tokens;
+        int step = 0;
+        for (; step + SAMP_UNROLL <= n_tokens; step += SAMP_UNROLL) FSMG_CUDA_OK(cudaGraphLaunch(h->samp_graph_multi, s));
+        for (; step < n_tokens; ++step) FSMG_CUDA_OK(cudaGraphLaunch(h->samp_graph, s));
+        h->launches += (int64_t)n_tokens * h->samp_step_launches;    // kernels executed (graph nodes), not host launches
     } else {
         for (int step = 0; step < n_tokens; ++step)
             if ((rc = sample_step_split(h, n, s))) return rc;
@@ -716,6 +727,7 @@ void fsmg_destroy(fsmg_handle* h) {
     if (h->h_scal) cudaFreeHost(h->h_scal);
     for (auto ev : h->prof.pool) cudaEventDestroy(ev);
     if (h->samp_graph) cudaGraphExecDestroy(h->samp_graph);
+    if (h->samp_graph_multi) cudaGraphExecDestroy(h->samp_graph_multi);
     for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
     for (int i = 0; i < 2; ++i) {
         if (h->aux[i]) cudaStreamDestroy(h->aux[i]);
@@ -780,6 +792,9 @@ int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, 
     }
     for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // graphs hold the old buffer addresses
     h->step_graphs.clear();
+    if (h->samp_graph) { cudaGraphExecDestroy(h->samp_graph); h->samp_graph = nullptr; }
+    if (h->samp_graph_multi) { cudaGraphExecDestroy(h->samp_graph_multi); h->samp_graph_multi = nullptr; }
+    h->samp_stale = true;
     h->bound = true;
     return FSMG_OK;
 }
