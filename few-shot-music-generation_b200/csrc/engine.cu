@@ -105,6 +105,7 @@ struct fsmg_handle {
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_dh[2] = {nullptr, nullptr}, ev_dws[2] = {nullptr, nullptr};
     int overlap = 1;
+    int dws_transposed = 1;  // softmax_w gradient accumulated as [V', H] (FSMG_DWS_T=0: [H, V'])
     int strip_overlap = 0;   // background softmax-gradient pass beside the dH / dWs GEMMs (FSMG_STRIP_OVERLAP=1; measured slower)
     int samp_max = 0;
     // pinned host staging
@@ -182,6 +183,8 @@ static void carve(fsmg_handle* h, char* base) {
     const char* env_mb = getenv("FSMG_CHUNK_MB");
     const char* env_ov = getenv("FSMG_OVERLAP");
     const char* env_gr = getenv("FSMG_GRAPH");
+    const char* env_dt = getenv("FSMG_DWS_T");
+    if (env_dt) h->dws_transposed = atoi(env_dt);
     const char* env_so = getenv("FSMG_STRIP_OVERLAP");
     h->strip_overlap = env_so ? atoi(env_so) : 0;   // measured: 14.17 ms (1 background CTA/SM: 1.2 TB/s) / 12.65 (6/SM) vs 12.47 serial
     h->use_graph = env_gr ? atoi(env_gr) : 1;
@@ -207,7 +210,8 @@ static void carve(fsmg_handle* h, char* base) {
     h->dlogits = b.take<__half>(rows * h->Vp);
     h->dlogits_b[0] = h->dlogits;
     h->dlogits_b[1] = b.take<__half>(rows * h->Vp);
-    h->dws_acc = b.take<float>((int64_t)h->H * h->Vp);   // dWs accumulated with 16-byte aligned rows (V' is odd)
+    // dWs accumulated with 16-byte aligned rows (V' is odd): [H, Vp], or transposed [V', Hq] (default, see projection())
+    { int64_t a = (int64_t)h->H * h->Vp, bt = (int64_t)h->V1 * round_up(h->H, 4); h->dws_acc = b.take<float>(a > bt ? a : bt); }
     // sampler (fp32 route)
     h->samp_max = h->Nmax;
     h->samp_ids = b.take<int32_t>(h->samp_max);
@@ -342,7 +346,26 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
     float* g_sb = h->grads ? h->grads + h->sb_off : nullptr;
     float* nll_out = d_nll_user ? d_nll_user : h->nll;
     const bool use_tc = !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) && tc_projection_supported(h->tc, H, h->V1);
-    if (train) FSMG_CUDA_OK(cudaMemsetAsync(h->dws_acc, 0, sizeof(float) * (size_t)H * h->Vp, s));
+    // dWs: computed TRANSPOSED by default, dWs^T[V', H] += dlogits^T * hs.  With H <= 512 that GEMM has a single (256 x 512 pair) N
+    // tile, so every dlogits element is fetched exactly once; the [H, V'] orientation read the chunk once per 256 rows of H (ncu: 766 MB
+    // of DRAM reads per 369 MB chunk, 69 % DRAM utilisation — the kernel had become HBM-bound).  One fp32 transpose per step undoes it.
+    const int Hq = (int)round_up(H, 4);
+    const bool dws_t = h->dws_transposed != 0;
+    if (train) FSMG_CUDA_OK(cudaMemsetAsync(h->dws_acc, 0, sizeof(float) * (size_t)(dws_t ? (int64_t)h->V1 * Hq : (int64_t)H * h->Vp), s));
+    auto dws_gemm = [&](const __half* hc_, const __half* dl_, int mc_, cudaStream_t st) {
+        if (dws_t) return gemm_f16(h, mk(h->V1, H, mc_, dl_, h->Vp, hc_, h->Hp, h->dws_acc, Hq, loss_scale, nullptr, 0, 0, 1), true, true, st);
+        return gemm_f16(h, mk(H, h->V1, mc_, hc_, h->Hp, dl_, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 0, 1), true, true, st);
+    };
+    auto dws_finish = [&](cudaStream_t st) {
+        if (dws_t) {
+            dim3 grid(cdiv(H, 32), cdiv(h->V1, 32));
+            transpose_f32_kernel<<<grid, dim3(32, 8), 0, st>>>(h->dws_acc, Hq, g_sw, h->V1, h->V1, H);
+        } else {
+            int64_t total = (int64_t)H * h->V1;
+            unpad_rows_kernel<<<cdiv(total, 256), 256, 0, st>>>(h->dws_acc, h->Vp, g_sw, h->V1, H, h->V1);
+        }
+        LAUNCH_COUNT(h);
+    };
     // overlap is switched off while profiling so that per-phase event brackets do not double count
     const bool overlap = train && use_tc && h->overlap && !h->prof.on && h->aux[0] != nullptr;
     // Optional training schedule (FSMG_STRIP_OVERLAP=1) on the tcgen05 route: the HBM-bound softmax-gradient pass of chunk i runs as a background kernel
@@ -381,14 +404,11 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
                 FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dh[buf], 0));     // dlogits of chunk j are final
                 rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits_b[buf], h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H, 1.0f, nullptr, 0, 0, 1), false, false, s);
                 if (rc) return rc;
-                rc = gemm_f16(h, mk(H, h->V1, mc, hs + r0 * h->Hp, h->Hp, h->dlogits_b[buf], h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 0, 1),
-                              true, true, s);
+                rc = dws_gemm(hs + r0 * h->Hp, h->dlogits_b[buf], mc, s);
                 if (rc) return rc;
             }
         }
-        int64_t total = (int64_t)H * h->V1;
-        unpad_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(h->dws_acc, h->Vp, g_sw, h->V1, H, h->V1);
-        LAUNCH_COUNT(h);
+        dws_finish(s);
         FSMG_LAUNCH_OK();
         return FSMG_OK;
     }
@@ -453,7 +473,7 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
         {
             ProfScope ps_dws(h, PH_DWS, s_dws);
             // accumulated across chunks with fire-and-forget vector reductions into the L2-resident buffer (no read latency in the epilogue)
-            rc = gemm_f16(h, mk(H, h->V1, mc, hc, h->Hp, h->dlogits, h->Vp, h->dws_acc, h->Vp, loss_scale, nullptr, 0, 0, 1), true, true, s_dws);
+            rc = dws_gemm(hc, h->dlogits, mc, s_dws);
         }
         if (rc) return rc;
         if (overlap) {
@@ -468,11 +488,7 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
         }
     }
     h->dlogits = h->dlogits_b[0];
-    if (train) {
-        int64_t total = (int64_t)H * h->V1;
-        unpad_rows_kernel<<<cdiv(total, 256), 256, 0, s>>>(h->dws_acc, h->Vp, g_sw, h->V1, H, h->V1);
-        LAUNCH_COUNT(h);
-    }
+    if (train) dws_finish(s);
     FSMG_LAUNCH_OK();
     return FSMG_OK;
 }

@@ -412,6 +412,21 @@ __global__ void unpad_rows_kernel(const float* __restrict__ src, int64_t lds, fl
     dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
 }
 
+// dst[c*ldd + r] = src[r*lds + c] : 32 x 32 tiles through shared memory, both sides coalesced
+__global__ void transpose_f32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * lds + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(int64_t)c * ldd + r] = tile[threadIdx.x][i];
+    }
+}
+
 // ============================================================================================
 // Split-fp16 operands for fp32-grade tensor-core contractions (greedy sampler):
 //   x = hi + 2^-11 * lo ,  hi = fp16(x) ,  lo = fp16((x - hi) * 2^11)      (about 22 mantissa bits)
