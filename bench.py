@@ -305,6 +305,27 @@ def main():
                passes_ms_per_step=[round(x, 4) for x in passes],
                h2d_bytes_per_step=n_seqs * T * 4, d2h_bytes_per_step=4)
 
+    # ---- same call with a device-resident corpus (data.device_episode): only song indices cross PCIe ------------
+    from data.device_episode import DeviceEpisodeSampler
+    from data.episode import TokenCorpus
+    rng_c = np.random.RandomState(99 + rank)
+    from data import synthetic as SY
+    songs = SY.synthetic_tokens(rng_c, (64, 24, T), w["input_size"], w["kind"])
+    dsamp = DeviceEpisodeSampler(TokenCorpus([songs[a] for a in range(64)], w["input_size"], T), 5, 5, 4, T, seed=7 + rank)
+    idx_batches = [[dsamp.get_episode() for _ in range(w["episodes"])] for _ in range(n_distinct)]
+    for i in range(2):
+        model.train(idx_batches[i % n_distinct])
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        model.train(idx_batches[i % n_distinct])    # indices -> pinned -> H2D -> device gather -> step -> D2H loss
+    ev1.record()
+    barrier()
+    ms_idx = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    e2e["device_corpus"] = dict(value=tokens_per_step / (ms_idx * 1e-3), unit="tokens/s", ms_per_step=ms_idx,
+                                h2d_bytes_per_step=n_seqs * 4, d2h_bytes_per_step=4,
+                                note="episodes as index sets into an HBM-resident corpus (data.device_episode), gathered on the device")
+
     # ---- per-phase device timing (CUDA events on the launching stream, 2 extra steps) ---------------
     eng.set_profile(True)
     eng.read_profile()

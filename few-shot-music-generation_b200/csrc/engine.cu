@@ -17,6 +17,7 @@
 #include "simt_kernels.cuh"
 #include "tc_gemm.cuh"
 #include "tc_lstm.cuh"
+#include "unigram.cuh"
 
 namespace fsmg {
 
@@ -1046,6 +1047,50 @@ int fsmg_debug_softmax_grad(int32_t rows, int32_t vocab1, int64_t ld, void* d_lo
     FSMG_CUDA_OK(cudaGetDevice(&dev));
     FSMG_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     return tc_softmax_grad_launch(sms, mode, param, waves, d_y, 0, rows, vocab1, (__half*)d_logits_f16, ld, d_lse, alpha, d_db, (cudaStream_t)stream);
+}
+
+// ---- device-side episode assembly -------------------------------------------------------------------------
+int fsmg_gather_token_rows(const int32_t* d_corpus, int64_t n_corpus_rows, int32_t row_len, const int32_t* d_row_ids, int32_t n_ids,
+                           int32_t* d_tokens_out, void* stream) {
+    if (!d_corpus || !d_row_ids || !d_tokens_out || n_corpus_rows <= 0 || row_len <= 0 || n_ids <= 0)
+        return set_error(FSMG_ERR_INVALID, "fsmg_gather_token_rows: bad argument");
+    if ((reinterpret_cast<uintptr_t>(d_corpus) & 15) || (reinterpret_cast<uintptr_t>(d_tokens_out) & 15))
+        return set_error(FSMG_ERR_INVALID, "fsmg_gather_token_rows: corpus and output must be 16-byte aligned");
+    gather_token_rows_kernel<<<cdiv(n_ids, 8), 256, 0, (cudaStream_t)stream>>>(d_corpus, n_corpus_rows, row_len, d_row_ids, n_ids, d_tokens_out);
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+// ---- unigram baseline (reference src/models/unigram_model.py) ------------------------------------------------------------
+int fsmg_unigram_step(float* d_counts, int32_t vocab, const int32_t* d_tokens, int32_t n_rows, int32_t row_len, int32_t col_begin,
+                      int32_t col_end, int32_t update, float* d_scratch4, float* d_mean_nll, void* stream) {
+    float* d_scratch2 = d_scratch4;
+    if ((reinterpret_cast<uintptr_t>(d_scratch4) & 7) != 0) return set_error(FSMG_ERR_INVALID, "fsmg_unigram_step: scratch must be 8-byte aligned");
+    if (!d_counts || !d_tokens || !d_scratch2 || !d_mean_nll) return set_error(FSMG_ERR_INVALID, "fsmg_unigram_step: null argument");
+    if (vocab <= 0 || n_rows <= 0 || row_len <= 0 || col_begin < 0 || col_end > row_len || col_begin >= col_end)
+        return set_error(FSMG_ERR_INVALID, "fsmg_unigram_step: bad shape (vocab=%d rows=%d row_len=%d cols=[%d,%d))", vocab, n_rows, row_len,
+                         col_begin, col_end);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = (int64_t)n_rows * (col_end - col_begin);
+    if (n <= (1 << 16)) {
+        unigram_fused_kernel<<<1, 1024, 0, s>>>(d_counts, vocab, d_tokens, n_rows, row_len, col_begin, col_end, update, d_mean_nll);
+    } else {
+        int sms = 148, dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        unigram_sum_kernel<<<1, 1024, 0, s>>>(d_counts, vocab, d_scratch2);
+        unigram_nll_kernel<<<sms * 4, 256, 0, s>>>(d_counts, d_tokens, n_rows, row_len, col_begin, col_end, d_scratch2);
+        unigram_update_kernel<<<sms * 4, 256, 0, s>>>(update ? d_counts : nullptr, d_tokens, n_rows, row_len, col_begin, col_end, d_scratch2,
+                                                      d_mean_nll);
+    }
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+int fsmg_unigram_argmax(const float* d_counts, int32_t vocab, int32_t* d_out, void* stream) {
+    if (!d_counts || !d_out || vocab <= 0) return set_error(FSMG_ERR_INVALID, "fsmg_unigram_argmax: bad argument");
+    unigram_argmax_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_counts, vocab, d_out);
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
 }
 
 }  // extern "C"

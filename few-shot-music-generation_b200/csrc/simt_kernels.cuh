@@ -412,6 +412,27 @@ __global__ void unpad_rows_kernel(const float* __restrict__ src, int64_t lds, fl
     dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
 }
 
+// Episode assembly on the device: out[i, :] = table[ids[i], :] for int32 token rows — the step's token batch is
+// gathered from a corpus that is resident in HBM, so only the song indices cross PCIe (reference data/episode.py:62-74 builds the
+// same [B, S+Q, T] arrays on the host, song by song).  One warp per row, 16-byte accesses when the row length allows.
+__global__ void gather_token_rows_kernel(const int32_t* __restrict__ table, int64_t n_table_rows, int row_len,
+                                         const int32_t* __restrict__ ids, int n_ids, int32_t* __restrict__ out) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_ids) return;
+    int64_t src = ids[row];
+    if (src < 0 || src >= n_table_rows) src = 0;      // ids are validated on the host; never read out of bounds
+    const int32_t* in = table + src * row_len;
+    int32_t* o = out + (int64_t)row * row_len;
+    if ((row_len & 3) == 0) {
+        const int4* in4 = reinterpret_cast<const int4*>(in);
+        int4* o4 = reinterpret_cast<int4*>(o);
+        for (int c = lane; c < (row_len >> 2); c += 32) o4[c] = in4[c];
+    } else {
+        for (int c = lane; c < row_len; c += 32) o[c] = in[c];
+    }
+}
+
 // dst[c*ldd + r] = src[r*lds + c] : 32 x 32 tiles through shared memory, both sides coalesced
 __global__ void transpose_f32_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int rows, int cols) {
     __shared__ float tile[32][33];

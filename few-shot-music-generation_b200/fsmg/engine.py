@@ -92,6 +92,7 @@ class Engine:
         self._pinned_tok = torch.empty(self.max_seqs * self.T, dtype=torch.int32).pin_memory()
         self._pinned_scal = torch.empty(8, dtype=torch.float32).pin_memory()
         self._h2d_done: Optional[torch.cuda.Event] = None
+        self._ids: Optional[torch.Tensor] = None
 
     # ---- parameters ---------------------------------------------------------------------------
     def param_shapes(self) -> Dict[str, tuple]:
@@ -187,6 +188,43 @@ class Engine:
             self._h2d_done = torch.cuda.Event()
         self._h2d_done.record(torch.cuda.current_stream(self.device))
         return dev.view(n, self.T)
+
+    # ---- device-resident corpus: only song indices cross PCIe ---------------------------
+    def _stage_indexed(self, corpus: torch.Tensor, row_ids: np.ndarray) -> torch.Tensor:
+        """corpus int32 [n_songs, T] on the device; row_ids [n] -> the step's token batch [n, T], gathered on the device."""
+        ids = np.ascontiguousarray(row_ids, dtype=np.int32).reshape(-1)
+        n = int(ids.size)
+        if n > self.max_seqs:
+            raise FsmgError(f"{n} sequences > engine capacity {self.max_seqs}")
+        assert corpus.dtype == torch.int32 and corpus.is_cuda and corpus.is_contiguous() and corpus.shape[1] == self.T
+        if n and (ids.min() < 0 or ids.max() >= corpus.shape[0]):
+            raise FsmgError("song index outside the corpus")
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        if self._ids is None:
+            self._ids = torch.empty(self.max_seqs, dtype=torch.int32, device=self.device)
+        self._pinned_tok[:n].copy_(torch.from_numpy(ids))
+        self._ids[:n].copy_(self._pinned_tok[:n], non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+        dev = self._tok[: n * self.T]
+        _lib.check(self.lib.fsmg_gather_token_rows(corpus.data_ptr(), int(corpus.shape[0]), self.T, self._ids.data_ptr(), n,
+                                                   dev.data_ptr(), self._stream()))
+        return dev.view(n, self.T)
+
+    def train_indexed(self, corpus: torch.Tensor, row_ids: np.ndarray, global_tokens: Optional[int] = None) -> float:
+        loss = self.train_step_device(self._stage_indexed(corpus, row_ids), global_tokens)
+        self._pinned_scal[:1].copy_(loss, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._pinned_scal[0])
+
+    def eval_indexed(self, corpus: torch.Tensor, row_ids: np.ndarray) -> float:
+        dev = self._stage_indexed(corpus, row_ids)
+        _, s = self.forward_nll(dev)
+        self._pinned_scal[:1].copy_(s, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._pinned_scal[0]) / (float(dev.numel()) + 1e-12)
 
     def train_host(self, tokens: np.ndarray, global_tokens: Optional[int] = None) -> float:
         loss = self.train_step_device(self._stage(tokens), global_tokens)

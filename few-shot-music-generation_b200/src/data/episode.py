@@ -136,5 +136,9 @@ def load_sampler_from_config(config):
         raise RuntimeError('unknown dataset "%s"' % kind)
     if len(corpus) < config['batch_size']:
         raise RuntimeError('split "%s" has %d artists < batch_size %d' % (config['split'], len(corpus), config['batch_size']))
+    if config.get('device_episodes', False):   # corpus resident in HBM, episodes are index sets (data/device_episode.py)
+        from data.device_episode import DeviceEpisodeSampler
+        return DeviceEpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
+                                    config['max_len'], seed=config.get('seed', None))
     return EpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
                           config['max_len'], seed=config.get('seed', None))

@@ -79,6 +79,20 @@ class LSTMBaseline(BaseModel):
     def _eval_tokens(episodes):
         return np.concatenate([flatten_first_two_dims(ep.query) for ep in episodes], axis=0)
 
+    @staticmethod
+    def _indexed(episodes):
+        """All episodes of the step index ONE device-resident corpus (data.device_episode.IndexedEpisode)?"""
+        first = getattr(episodes[0], 'sampler', None)
+        return first is not None and all(getattr(ep, 'sampler', None) is first and hasattr(ep, 'support_ids') for ep in episodes)
+
+    @staticmethod
+    def _train_ids(episodes):
+        rows = []
+        for ep in episodes:  # same row order as _train_tokens
+            rows.append(np.asarray(ep.support_ids).reshape(-1))
+            rows.append(np.asarray(ep.query_ids).reshape(-1))
+        return np.concatenate(rows)
+
     def _ensure_init(self):
         if not self._initialized:
             self.recover_or_init('')
@@ -87,7 +101,11 @@ class LSTMBaseline(BaseModel):
     def train(self, episode):
         """Concatenate support and query sets and take one optimizer step; returns the loss."""
         self._ensure_init()
-        loss = self._engine.train_host(self._train_tokens(_as_list(episode)))
+        episodes = _as_list(episode)
+        if self._indexed(episodes):   # device-resident corpus: only the song indices are uploaded
+            loss = self._engine.train_indexed(episodes[0].corpus_device, self._train_ids(episodes))
+        else:
+            loss = self._engine.train_host(self._train_tokens(episodes))
         if self._summary_writer:
             self._summary_writer.add_scalar('Train/loss', loss, self._train_calls)
         self._train_calls += 1
@@ -96,7 +114,12 @@ class LSTMBaseline(BaseModel):
     def eval(self, episode):
         """Ignore the support set and evaluate only on the query set; returns mean NLL."""
         self._ensure_init()
-        avg_neg_log = self._engine.eval_host(self._eval_tokens(_as_list(episode)))
+        episodes = _as_list(episode)
+        if self._indexed(episodes):
+            ids = np.concatenate([np.asarray(ep.query_ids).reshape(-1) for ep in episodes])
+            avg_neg_log = self._engine.eval_indexed(episodes[0].corpus_device, ids)
+        else:
+            avg_neg_log = self._engine.eval_host(self._eval_tokens(episodes))
         if self._summary_writer is not None:
             self._summary_writer.add_scalar('Eval/Avg_NLL', avg_neg_log, self._eval_calls)
         self._eval_calls += 1

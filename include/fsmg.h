@@ -160,6 +160,28 @@ int fsmg_debug_softmax_grad(int32_t rows, int32_t vocab1, int64_t ld, void* d_lo
                             const int32_t* d_y, float alpha, float* d_db, int32_t mode, int32_t param, int32_t waves,
                             void* stream);
 
+/* ---- device-side episode assembly (replaces the host loop of EpisodeSampler.get_episode, reference
+ * src/data/episode.py:62-74, once the tokenised corpus is resident in HBM) ---------------------------------------------
+ * d_corpus is int32 [n_corpus_rows, row_len] (every song of the split, zero-padded to max_len like
+ * base_loader.py:52-64); d_row_ids are the n_ids song rows of the step in batch order; d_tokens_out [n_ids, row_len]
+ * is then a valid `tokens` argument for fsmg_forward_nll / fsmg_forward_backward.  Only the indices cross PCIe. */
+int fsmg_gather_token_rows(const int32_t* d_corpus, int64_t n_corpus_rows, int32_t row_len, const int32_t* d_row_ids,
+                           int32_t n_ids, int32_t* d_tokens_out, void* stream);
+
+/* ---- unigram baseline: the reference's second registered model (src/models/unigram_model.py) -------------------------
+ * d_counts is the `word_count` variable (:27-30: fp32 [vocab], initialised to alpha = 1 by the caller, not trainable).
+ * fsmg_unigram_step replaces sess.run([train_op, avg_neg_log]) of train() (:41-55, update = 1, words = tokens[:, 0:T-1])
+ * and sess.run(avg_neg_log) of eval() (:57-67, update = 0, words = tokens[:, 1:T]):
+ *     *d_mean_nll = -mean(log(word_count[w] / sum(word_count)))  over tokens[:, col_begin:col_end]   (:35-37)
+ *     then, if update: word_count[w] += 1 per occurrence                                              (:31-33)
+ * The loss is taken on the counts BEFORE the update (TF1 leaves the order unspecified).  d_tokens is int32
+ * [n_rows, row_len]; d_scratch4 is 4 floats (8-byte aligned) of device scratch.  fsmg_unigram_argmax replaces sample()'s
+ * np.argmax(prob_all) (:69-78): first maximal index. */
+int fsmg_unigram_step(float* d_counts, int32_t vocab, const int32_t* d_tokens, int32_t n_rows, int32_t row_len,
+                      int32_t col_begin, int32_t col_end, int32_t update, float* d_scratch4, float* d_mean_nll,
+                      void* stream);
+int fsmg_unigram_argmax(const float* d_counts, int32_t vocab, int32_t* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -221,3 +221,27 @@ def test_package_synthetic_generator_matches_oracle_generator():
         a = S.synthetic_episode(np.random.RandomState(5), 5, 5, 4, 32, vocab, kind)
         b = O.synthetic_episode(np.random.RandomState(5), 5, 5, 4, 32, vocab, kind)
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_device_episode_sampler_draws_the_same_episodes_as_the_host_sampler():
+    """Same seed -> same artists and songs: IndexedEpisode.support/.query (materialised from the index sets) equal the
+    arrays EpisodeSampler.get_episode builds; row order of the train batch is support rows then query rows."""
+    from data.device_episode import DeviceEpisodeSampler
+    from data.episode import load_sampler_from_config
+    cfg = dict(dataset="synthetic_lyrics", dataset_path=".", split="train", batch_size=5, support_size=5, query_size=4,
+               max_len=16, synthetic_vocab=300, synthetic_artists=12, synthetic_songs_per_artist=11, seed=77)
+    host = load_sampler_from_config(dict(cfg))
+    dev = load_sampler_from_config(dict(cfg, device_episodes=True))
+    assert isinstance(dev, DeviceEpisodeSampler)
+    for _ in range(5):
+        a, b = host.get_episode(), dev.get_episode()
+        assert b.support_ids.shape == (5, 5) and b.query_ids.shape == (5, 4)
+        assert np.array_equal(a.support, b.support) and np.array_equal(a.query, b.query)
+        assert np.array_equal(dev.corpus_host[b.support_ids.reshape(-1)], a.support.reshape(-1, 16))
+    # wrapping an existing sampler continues its RNG stream
+    wrapped = DeviceEpisodeSampler.from_sampler(host)
+    nxt_host = load_sampler_from_config(dict(cfg))
+    for _ in range(5):
+        nxt_host.get_episode()
+    a, b = nxt_host.get_episode(), wrapped.get_episode()
+    assert np.array_equal(a.support, b.support) and np.array_equal(a.query, b.query)

@@ -265,3 +265,31 @@ def test_sampling_after_training_uses_fresh_weights(torch_cuda):
             assert margins[i] < TIE_MARGIN, (i, a, b, margins[i])
             break
     assert before != after or before == want
+
+
+def test_device_resident_corpus_training_equals_host_episode_training(torch_cuda):
+    """episodes drawn as index sets into a corpus resident in HBM and gathered on the device give exactly
+    the losses of the same episodes assembled on the host (reference data/episode.py:62-74) — only indices cross PCIe."""
+    from data.episode import load_sampler_from_config
+    from train.train import load_model_from_config
+    data = dict(dataset="synthetic_lyrics", dataset_path=".", split="train", batch_size=5, support_size=5, query_size=4,
+                max_len=12, synthetic_vocab=200, synthetic_artists=9, synthetic_songs_per_artist=10, seed=5)
+    host = load_sampler_from_config(dict(data))
+    dev = load_sampler_from_config(dict(data, device_episodes=True))
+    cfg = _plugin_config(episodes_per_step=2)
+    m_host, m_dev = load_model_from_config(cfg), load_model_from_config(cfg)
+    m_host.recover_or_init("")
+    m_dev.recover_or_init("")
+    close = lambda a, b: abs(a - b) <= 1e-5 * abs(b)      # gradient REDs are order-dependent: the two models drift by ulps
+    for step in range(4):
+        eh = [host.get_episode() for _ in range(2)]
+        ed = [dev.get_episode() for _ in range(2)]
+        if step == 0:
+            assert m_dev.eval(ed) == m_host.eval(eh)      # identical weights and tokens -> identical forward
+        assert close(m_dev.eval(ed), m_host.eval(eh))
+        assert close(m_dev.train(ed), m_host.train(eh))
+    # single episodes (the reference's call pattern) and mixing with host episodes
+    assert close(m_dev.train(dev.get_episode()), m_host.train(host.get_episode()))
+    e1, e2 = dev.get_episode(), host.get_episode()
+    assert np.array_equal(e1.support, e2.support)
+    assert close(m_dev.train([e1, e2]), m_host.train([e2, e2]))      # mixed list falls back to host assembly
