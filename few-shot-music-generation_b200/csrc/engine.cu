@@ -85,6 +85,12 @@ struct fsmg_handle {
     int32_t *x_ids = nullptr, *y_ids = nullptr, *tok_stage = nullptr, *tok_graph = nullptr, *samp_ids = nullptr, *samp_out = nullptr, *samp_out2 = nullptr;
     __half *emb16 = nullptr, *Ws16 = nullptr, *WsT16 = nullptr, *xemb = nullptr, *dgates = nullptr, *dlogits = nullptr;
     __half* pre16 = nullptr;   // hoisted x*Wx+b, fp16 [NT, G4p]
+    __half* pre_tab = nullptr; // embedding*Wx+b for every word, fp16 [V', G4p]
+    int pre_table = 1;         // FSMG_PRE_TABLE=0: always the per-token GEMM
+    int32_t *tok_counts = nullptr, *sorted_rows = nullptr, *sorted_tok = nullptr;
+    float* seg32 = nullptr;
+    __half* seg16 = nullptr;
+    int seg_grad = 1;          // FSMG_SEG_GRAD=0: per-token weight-gradient GEMM + scatter epilogue for the layer-0 input side
     float *gbuf = nullptr, *dact[2] = {nullptr, nullptr}, *dh_rec = nullptr, *dc_next = nullptr, *logits32 = nullptr;
     float *lse = nullptr, *nll = nullptr, *scalars = nullptr, *dws_acc = nullptr;
     float *s_x = nullptr, *s_g = nullptr, *s_logits = nullptr;
@@ -163,6 +169,13 @@ static void carve(fsmg_handle* h, char* base) {
     h->WsT16 = b.take<__half>((int64_t)h->V1 * h->Hp);
     h->xemb = b.take<__half>(NT * h->Ep);
     h->pre16 = b.take<__half>(NT * h->G4p);
+    h->pre_tab = b.take<__half>((int64_t)h->V1 * h->G4p);   // per-word pre-activation table of layer 0 (see forward_lstm)
+    // token-sorted segment sums of dgates (layer-0 input gradients, see backward_lstm)
+    h->tok_counts = b.take<int32_t>(3 * ((int64_t)h->V1 + 8));
+    h->sorted_rows = b.take<int32_t>(NT);
+    h->sorted_tok = b.take<int32_t>(NT);
+    h->seg32 = b.take<float>((int64_t)h->V1 * h->G4);
+    h->seg16 = b.take<__half>((int64_t)h->V1 * h->G4p);
     h->gbuf = b.take<float>((int64_t)h->Nmax * h->G4);   // per-step route: recurrent contraction of one step
     h->dgates = b.take<__half>(NT * h->G4p);
     int wmax = h->E > h->H ? h->E : h->H;
@@ -184,6 +197,10 @@ static void carve(fsmg_handle* h, char* base) {
     const char* env_mb = getenv("FSMG_CHUNK_MB");
     const char* env_ov = getenv("FSMG_OVERLAP");
     const char* env_gr = getenv("FSMG_GRAPH");
+    const char* env_sg = getenv("FSMG_SEG_GRAD");
+    if (env_sg) h->seg_grad = atoi(env_sg);
+    const char* env_pt = getenv("FSMG_PRE_TABLE");
+    if (env_pt) h->pre_table = atoi(env_pt);
     const char* env_dt = getenv("FSMG_DWS_T");
     if (env_dt) h->dws_transposed = atoi(env_dt);
     const char* env_so = getenv("FSMG_STRIP_OVERLAP");
@@ -291,33 +308,55 @@ static int refresh_weights(fsmg_handle* h, cudaStream_t s) {
 }
 
 // ---- forward through the LSTM stack (embedding -> layers), stashing what BPTT needs -----------
-static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, cudaStream_t s) {
+// layer 0 handled per WORD instead of per token (pre-activation table forward, segment sums backward)?
+static bool layer0_word_forward(fsmg_handle* h, int N) {
+    return !(h->cfg.flags & (FSMG_FLAG_SIMT_RECURRENT | FSMG_FLAG_SIMT_GEMM)) && tc_recurrent_supported(h->tc, N, h->H) && h->pre_table &&
+           (int64_t)h->V1 < (int64_t)N * h->T;
+}
+static bool layer0_word_backward(fsmg_handle* h, int N) {
+    return !(h->cfg.flags & (FSMG_FLAG_SIMT_RECURRENT | FSMG_FLAG_SIMT_GEMM)) && tc_recurrent_supported(h->tc, N, h->H) && h->seg_grad &&
+           (int64_t)h->V1 < (int64_t)N * h->T && h->Ep == h->E;
+}
+
+static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, bool train, cudaStream_t s) {
     const int T = h->T, H = h->H, TB = 256;
     const int64_t NT = (int64_t)N * T;
     {
     ProfScope ps(h, PH_PREP, s);
     prep_tokens_kernel<<<cdiv(NT, TB), TB, 0, s>>>(d_tokens, h->x_ids, h->y_ids, N, T, h->V, h->V);
     LAUNCH_COUNT(h);
-        int cols8 = h->Ep / 8;
-        gather_rows_f16_kernel<<<cdiv(NT * cols8, TB), TB, 0, s>>>(h->emb16, h->Ep, h->x_ids, h->xemb, h->Ep, NT, cols8);
-        LAUNCH_COUNT(h);
+        // the gathered embedding rows are only needed by the per-token input GEMM (forward) / weight-gradient GEMM (backward)
+        if (!layer0_word_forward(h, N) || (train && !layer0_word_backward(h, N))) {
+            int cols8 = h->Ep / 8;
+            gather_rows_f16_kernel<<<cdiv(NT * cols8, TB), TB, 0, s>>>(h->emb16, h->Ep, h->x_ids, h->xemb, h->Ep, NT, cols8);
+            LAUNCH_COUNT(h);
+        }
     }
     FSMG_LAUNCH_OK();
     for (int li = 0; li < h->L; ++li) {
         LayerBuf& l = h->layers[li];
         const __half* in = li == 0 ? h->xemb : h->layers[li - 1].hs;
         const float* bias = h->params + l.b_off;
-        // hoisted input contraction: pre[NT,4H] = in[NT,in] * Wx + b   (K3 in SURVEY §2.1)
+        // hoisted input contraction (K3 in SURVEY §2.1): pre[NT,4H] = in[NT,in] * Wx + b — or, for layer 0 on the persistent route
+        // when the batch holds more tokens than the vocabulary has words, the per-WORD table P[V',4H] = embedding * Wx + b (one small
+        // GEMM: 10 001 rows instead of 184 320 at cfg 2) that the recurrent kernel reads through the input ids.  Same operands, same
+        // K order, same fp16 rounding: bit-identical pre-activations, without the [NT,4H] write + read and 95 % of the GEMM.
+        const bool persistent_fwd = !(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
+                                    tc_recurrent_supported(h->tc, N, H);
+        const bool word_table = li == 0 && layer0_word_forward(h, N);
         int rc;
         {
             ProfScope ps(h, PH_INPUT_GEMM, s);
-            rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre16, h->G4p, 1.0f, bias, /*c_half=*/1), false, false, s);
+            if (word_table)
+                rc = gemm_f16(h, mk(h->V1, h->G4, l.in, h->emb16, h->Ep, l.WxT16, l.inp, h->pre_tab, h->G4p, 1.0f, bias, /*c_half=*/1), false, false, s);
+            else
+                rc = gemm_f16(h, mk((int)NT, h->G4, l.in, in, l.inp, l.WxT16, l.inp, h->pre16, h->G4p, 1.0f, bias, /*c_half=*/1), false, false, s);
         }
         if (rc) return rc;
         ProfScope ps_rec(h, PH_REC_FWD, s);
-        if (!(h->cfg.flags & FSMG_FLAG_SIMT_RECURRENT) && !(h->cfg.flags & FSMG_FLAG_SIMT_GEMM) &&
-            tc_recurrent_supported(h->tc, N, H)) {
-            rc = tc_lstm_forward(h->tc, h->pre16, l.WhT16, l.gates, l.c, l.hs, N, T, H, h->Hp, h->G4p, s);
+        if (persistent_fwd) {
+            rc = tc_lstm_forward(h->tc, word_table ? h->pre_tab : h->pre16, word_table ? h->x_ids : nullptr, l.WhT16, l.gates, l.c, l.hs, N, T, H,
+                                 h->Hp, h->G4p, s);
             LAUNCH_COUNT(h);
             if (rc) return rc;
             continue;
@@ -527,6 +566,55 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
             }
             FSMG_LAUNCH_OK();
         }
+        }
+        // Layer-0 input side through token-sorted segment sums S[v,:] = sum_{x[r]=v} dgates[r,:] when the batch holds more tokens than
+        // the vocabulary has words (persistent tcgen05 route): bias gradient = column sums of S (82 MB instead of 755 MB at cfg 2),
+        // dK[:E] = embedding^T * S and dEmbedding = S * K[:E]^T over V' rows instead of N*T tokens; the per-token dX GEMM survives
+        // only as the per-occurrence square norm of TF's clip — an epilogue without a single global write.
+        const bool seg = li == 0 && persistent && layer0_word_backward(h, N);
+        if (seg) {
+            ProfScope ps_seg(h, PH_WGRAD, s);
+            const int V1 = h->V1;
+            int32_t* counts = h->tok_counts;
+            int32_t* offsets = counts + (V1 + 8);
+            int32_t* cursor = offsets + (V1 + 8);
+            FSMG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(V1 + 8), s));
+            token_hist_kernel<<<cdiv(NT, TB), TB, 0, s>>>(h->x_ids, NT, counts);
+            token_scan_kernel<<<1, 1024, 0, s>>>(counts, V1, offsets, cursor);
+            token_fill_kernel<<<cdiv(NT, TB), TB, 0, s>>>(h->x_ids, NT, cursor, h->sorted_rows, h->sorted_tok);
+            FSMG_CUDA_OK(cudaMemsetAsync(h->seg32, 0, sizeof(float) * (size_t)V1 * h->G4, s));
+            constexpr int RPB = 64;
+            segsum_rows_kernel<RPB><<<dim3(cdiv(h->G4, 1024), cdiv(NT, RPB)), 128, 0, s>>>(h->dgates, h->G4p, h->G4, h->sorted_tok, h->sorted_rows, NT,
+                                                                                          h->seg32, h->G4);
+            // fp16 operand copy of S + db = loss_scale * colsum(S)  (= colsum(dgates))
+            seg_finish_kernel<64><<<dim3(cdiv(h->G4p, 1024), cdiv(V1, 64)), 128, 0, s>>>(h->seg32, h->G4, V1, h->G4, h->seg16, h->G4p, loss_scale,
+                                                                                        h->grads + l.b_off);
+            h->launches += 5;
+            FSMG_LAUNCH_OK();
+            float* gK0 = h->grads + l.k_off;
+            // dK[:E] = loss_scale * embedding^T * S   (contraction over the V' words)
+            rc = gemm_f16(h, mk(l.in, h->G4, V1, h->emb16, h->Ep, h->seg16, h->G4p, gK0, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
+            if (rc) return rc;
+            // dK[E:] = loss_scale * h_{t-1}^T * dgates_t  (unchanged: contraction over the tokens)
+            if (T > 1) {
+                rc = gemm_f16(h, mk(H, h->G4, (int)(NT - N), l.hs, h->Hp, h->dgates + (int64_t)N * h->G4p, h->G4p,
+                                    gK0 + (int64_t)l.in * h->G4, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
+                if (rc) return rc;
+            }
+            // dEmbedding = loss_scale * S * K[:E]^T   (dense [V', E]; rows of words absent from the batch come out zero)
+            rc = gemm_f16(h, mk(V1, h->E, h->G4, h->seg16, h->G4p, l.K16, h->G4p, h->grads + h->emb_off, h->E, loss_scale), false, false, s);
+            if (rc) return rc;
+        }
+        if (seg) {
+            // per-occurrence square norm of the IndexedSlices rows: ||loss_scale * dgates[r,:] * K[:E]^T||^2 summed over tokens (A.6)
+            ProfScope ps_dx(h, PH_DX, s);
+            GemmArgs gn = mk((int)NT, l.in, h->G4, h->dgates, h->G4p, l.K16, h->G4p, nullptr, l.in);
+            gn.alpha = loss_scale;
+            rc = tc_gemm_scatter(h->tc, gn, h->x_ids, nullptr, h->E, h->grads + h->n_params + 1, s);
+            LAUNCH_COUNT(h);
+            if (rc) return rc;
+            cur ^= 1;
+            continue;
         }
         // db = loss_scale * colsum(dgates)
         ProfScope* ps_w = new ProfScope(h, PH_WGRAD, s);
@@ -826,7 +914,7 @@ int fsmg_forward_nll(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, fl
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     h->launches = 0;
-    rc = forward_lstm(h, d_tokens, n_seqs, s);
+    rc = forward_lstm(h, d_tokens, n_seqs, false, s);
     if (rc) return rc;
     rc = projection(h, n_seqs, false, 0.0f, d_nll, s);
     if (rc) return rc;
@@ -842,7 +930,7 @@ int fsmg_forward_nll(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, fl
 static int enqueue_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, float loss_scale, float* d_nll, cudaStream_t s) {
     h->launches = 0;
     FSMG_CUDA_OK(cudaMemsetAsync(h->grads, 0, sizeof(float) * (h->n_params + FSMG_GRAD_EXTRA), s));
-    int rc = forward_lstm(h, d_tokens, n_seqs, s);
+    int rc = forward_lstm(h, d_tokens, n_seqs, true, s);
     if (rc) return rc;
     rc = projection(h, n_seqs, true, loss_scale, d_nll, s);
     if (rc) return rc;

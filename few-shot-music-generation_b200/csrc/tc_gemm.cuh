@@ -619,6 +619,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int k = 0; k < 4; ++k) {
                             const int grow = row_w0 + 8 * k + (lane >> 2);
                             if (grow >= sh.M) continue;
+                            if (C == nullptr) {     // norm only: the dense gradient comes from the token-sorted segment sums
+                                if (full) sq_acc += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+                                else {
+                                    const float e4[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e)
+                                        if (colv + e < sh.N) sq_acc += e4[e] * e4[e];
+                                }
+                                continue;
+                            }
                             float* dst = C + (int64_t)ep.y[ep.row0 + grow] * ep.ldc + colv;
                             if (vec) {
                                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[k].x), "f"(v[k].y), "f"(v[k].z), "f"(v[k].w) : "memory");
@@ -1383,7 +1393,7 @@ static inline int tc_gemm_scatter(TcContext& c, const GemmArgs& g, const int32_t
     tc::EpiParams ep;
     memset(&ep, 0, sizeof ep);
     ep.C = table; ep.ldc = ld_table; ep.alpha = g.alpha; ep.y = ids; ep.row0 = 0; ep.tgt = occ_sq;
-    ep.vec_ok = ((reinterpret_cast<uintptr_t>(table) & 15) == 0 && (ld_table % 4) == 0) ? 1 : 0;
+    ep.vec_ok = (table && (reinterpret_cast<uintptr_t>(table) & 15) == 0 && (ld_table % 4) == 0) ? 1 : 0;
     CUtensorMap ma, mb;
     int rc = tc_make_maps(c, g, false, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;

@@ -110,6 +110,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 struct LstmParams {
     // forward
     const __half* pre;     // [T*N, G4p] fp16: x_t * Wx + b (hoisted input contraction; fp16 storage changes the NLL error by < 1e-5)
+    const int32_t* pre_ids; // null: row r of `pre` belongs to token r.  Else `pre` is a per-WORD table [V', G4p] (embedding * Wx + b
+                            // for every word, one small GEMM per step) and token r reads row pre_ids[r] (time-major input ids)
     // backward
     const float* dh_out;   // [T*N, H] fp32: dL/dh_t from above (projection or upper layer), unscaled
     __half* dgates;        // [T*N, G4p] fp16 out (also the exchanged operand)
@@ -126,6 +128,16 @@ struct LstmParams {
     int n_rows;            // sequences handled by this launch
     int rotate;            // walk the K chunks in an order rotated per loader (FSMG_LSTM_ROT bit 0: backward, bit 1: forward)
 };
+
+// first element of the hoisted pre-activation row of token (t, row): direct, or through the per-word table
+__device__ __forceinline__ const __half* lstm_pre_row(const LstmParams& p, int t, int row) {
+    const int64_t r = (int64_t)t * p.N + row;
+    return p.pre + (p.pre_ids ? (int64_t)__ldg(p.pre_ids + r) : r) * p.G4p;
+}
+// table rows are re-read by many tokens (keep them in L2); per-token rows are read exactly once (streaming)
+__device__ __forceinline__ uint4 lstm_pre_load(const LstmParams& p, const __half* ptr) {
+    return p.pre_ids ? __ldg(reinterpret_cast<const uint4*>(ptr)) : __ldcs(reinterpret_cast<const uint4*>(ptr));
+}
 
 __host__ __device__ constexpr int lstm_threads(int mt) { return 64 + 128 * mt; }   // producer warp, MMA warp, 4 epilogue warps per row tile
 constexpr int LSTM_MAX_DYN = 227 * 1024;
@@ -299,14 +311,14 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
             {
                 const int lrow = mt * 128 + quad * 32 + lane;
                 const bool ok = lrow < rows;
-                const __half* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * p.G4p + ju * U;
+                const __half* pre = ok ? lstm_pre_row(p, t, row_base + lrow) + ju * U : p.pre;
                 const uint32_t t_row = tmem_base + (uint32_t)((t & 1) * BUF_COLS) + q_idx * NCOL + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint32_t rr[U];
 #pragma unroll
                     for (int e = 0; e < U; e += 8) {
-                        uint4 raw = ok ? __ldcs(reinterpret_cast<const uint4*>(pre + q * p.H + e)) : make_uint4(0, 0, 0, 0);
+                        uint4 raw = ok ? lstm_pre_load(p, pre + q * p.H + e) : make_uint4(0, 0, 0, 0);
                         const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
                         for (int w = 0; w < 4; ++w) {
@@ -333,7 +345,7 @@ lstm_fwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     {
                         const int lrow = mt * 128 + quad * 32 + lane;
                         if (lrow < rows) {
-                            const __half* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * p.G4p + ju * U;
+                            const __half* nxt = lstm_pre_row(p, t + 2, row_base + lrow) + ju * U;
 #pragma unroll
                             for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
                         }
@@ -552,14 +564,14 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         for (int u = 0; u < US; ++u) c_state[u] = 0.0f;
         uint32_t tf_phase = 0;
         auto stage_pre = [&](int t) {
-            const __half* pre = p.pre + ((int64_t)t * p.N + row_base + lrow) * p.G4p + ucol;
+            const __half* pre = ok ? lstm_pre_row(p, t, row_base + lrow) + ucol : p.pre;
             const uint32_t t_row = tmem_base + (uint32_t)((hs_ * 2 + (t & 1)) * NCOL) + us * US + ((uint32_t)(quad * 32) << 16);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t rr[US];
 #pragma unroll
                 for (int e = 0; e < US; e += 8) {
-                    uint4 raw = ok ? __ldcs(reinterpret_cast<const uint4*>(pre + q * p.H + e)) : make_uint4(0, 0, 0, 0);
+                    uint4 raw = ok ? lstm_pre_load(p, pre + q * p.H + e) : make_uint4(0, 0, 0, 0);
                     const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
                     for (int w = 0; w < 4; ++w) {
@@ -581,7 +593,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                 if (lane == 0) mbar_arrive(&pre_ready[hs_ * 2 + ((t + 1) & 1)]);
                 if (tracer) FSMG_TR(t, 4);
                 if (t + 2 < p.T && ok) {
-                    const __half* nxt = p.pre + ((int64_t)(t + 2) * p.N + row_base + lrow) * p.G4p + ucol;
+                    const __half* nxt = lstm_pre_row(p, t + 2, row_base + lrow) + ucol;
 #pragma unroll
                     for (int q = 0; q < 4; ++q) prefetch_l2(nxt + q * p.H);
                 }
@@ -1093,8 +1105,8 @@ static inline bool tc_recurrent_supported(TcContext& c, int N, int H) {
 }
 
 // pre [T*N,4H] fp32, WhT16 [4H,Hp] fp16 -> gates [T*N,G4p], c [T*N,H], hs [T*N,Hp]
-static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half* WhT16, __half* gates, float* cbuf, __half* hs, int N,
-                                  int T, int H, int Hp, int G4p, cudaStream_t s) {
+static inline int tc_lstm_forward(TcContext& c, const __half* pre, const int32_t* pre_ids, const __half* WhT16, __half* gates, float* cbuf,
+                                  __half* hs, int N, int T, int H, int Hp, int G4p, cudaStream_t s) {
     LstmPlan pl = lstm_plan(c, N, H, (c.lstm_pair & 2) != 0);
     if (!pl.ok) return set_error(-1, "persistent LSTM: unsupported shape N=%d H=%d", N, H);
     CUtensorMap mw, mh;
@@ -1116,7 +1128,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const __half*
         FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
         tc::LstmParams p;
         memset(&p, 0, sizeof p);
-        p.pre = pre; p.gates = gates; p.c = cbuf; p.hs = hs; p.counters = c.counters; p.rotate = (c.lstm_rot & 2) != 0;
+        p.pre = pre; p.pre_ids = pre_ids; p.gates = gates; p.c = cbuf; p.hs = hs; p.counters = c.counters; p.rotate = (c.lstm_rot & 2) != 0;
         p.N = N; p.T = T; p.H = H; p.Hp = Hp; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
         const int w_bytes = (H / 64) * 4 * pl.U * 128;
