@@ -36,6 +36,8 @@ CASES = [
     (1440, 3, 64, 512, 1),          # BASELINE configs[1] batch: 9 groups x 160 rows, MT=2
     (2400, 3, 64, 512, 1),          # larger than one launch can hold: batch slicing
     (45, 4, 64, 1024, 1),           # H=1024: U=16, 64 CTAs per group
+    (300, 4, 64, 128, 2),           # N*T > V': layer 0 per word (pre-activation table + segment-sum gradients) under a second layer
+    (300, 4, 100, 128, 1),          # E % 8 != 0: table forward, per-token gradient path backward
 ]
 
 
