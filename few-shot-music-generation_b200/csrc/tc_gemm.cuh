@@ -547,7 +547,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const bool row_ok = row < sh.M;
             const int cb = n_blk * BN + cg * GCOLS;                // first column of this warp
             const uint32_t t_row = tmem_base + acc * BN + cg * GCOLS + ((uint32_t)(quad * 32) << 16);
-            float run_max = -INFINITY, run_sum = 0.0f;
+            // EPI_LSE: every 16-column chunk keeps its OWN (max, sum exp(v - max)); the pairs are merged after the loop.  A running
+            // (max, sum) would chain the chunks (chunk c+1's exponentials wait for chunk c's max): with only four warps per SM
+            // sub-partition that dependency, not the issue or MUFU rate, bounded the epilogue.
+            float cmx[CHUNKS], csm[CHUNKS];
+#pragma unroll
+            for (int cc = 0; cc < CHUNKS; ++cc) { cmx[cc] = -INFINITY; csm[cc] = 0.0f; }
             float sq_acc = 0.0f;
             int tgt_col = -1;
             if (EPI == EPI_LSE && row_ok) tgt_col = ep.y[ep.row0 + row] - cb;
@@ -733,8 +738,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         for (int j = 0; j < CW; ++j) tv = (j == tj) ? v[j] : tv;
                         ep.tgt[row] = tv;
                     }
-                    const float nmax = fmaxf(run_max, cmax);
-                    const float nmax_l2 = nmax * 1.4426950408889634f;
+                    const float nmax_l2 = cmax * 1.4426950408889634f;
                     float sa0 = 0.0f, sa1 = 0.0f, sa2 = 0.0f, sa3 = 0.0f;   // independent chains
 #pragma unroll
                     for (int j = 0; j < CW; j += 4) {
@@ -743,8 +747,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         sa2 += fast_ex2(fmaf(v[j + 2], 1.4426950408889634f, -nmax_l2));
                         sa3 += fast_ex2(fmaf(v[j + 3], 1.4426950408889634f, -nmax_l2));
                     }
-                    run_sum = run_sum * __expf(run_max - nmax) + ((sa0 + sa1) + (sa2 + sa3));
-                    run_max = nmax;
+                    cmx[cc] = cmax;
+                    csm[cc] = (sa0 + sa1) + (sa2 + sa3);
                     if (ep.logits16 && row_ok) {
                         // fp16 logits for the backward: this lane's 16 columns are 32 contiguous bytes of its row = one full sector:
                         // ONE 256-bit store, no smem transpose (the staged variant spent a third of the chunk's stall samples on
@@ -769,7 +773,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                 }
             }
-            if (EPI == EPI_LSE && row_ok) ep.part[(int64_t)row * ep.n_tiles_total + n_blk * 4 + cg] = make_float2(run_max, run_sum);
+            if (EPI == EPI_LSE && row_ok) {
+                float gmax = cmx[0];
+#pragma unroll
+                for (int cc = 1; cc < CHUNKS; ++cc) gmax = fmaxf(gmax, cmx[cc]);
+                float gsum = 0.0f;
+                if (gmax > -INFINITY) {
+#pragma unroll
+                    for (int cc = 0; cc < CHUNKS; ++cc)    // chunks past the last column carry (-inf, 0): ex2(-inf) = 0
+                        gsum += csm[cc] * fast_ex2((cmx[cc] - gmax) * 1.4426950408889634f);
+                }
+                ep.part[(int64_t)row * ep.n_tiles_total + n_blk * 4 + cg] = make_float2(gmax, gsum);
+            }
             if (EPI == EPI_SCATTER) {
                 sq_acc = warp_sum(sq_acc);
                 if (lane == 0 && sq_acc != 0.0f) atomicAdd(ep.tgt, sq_acc);

@@ -1,1 +1,3 @@
-bash profiles/ab.sh r2i "-" "FSMG_ASTAT=1" "-" "FSMG_ASTAT=1"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+bash profiles/ab.sh r2k "-" "-"
+python profiles/eval_phases.py 2>&1 | tail -2
