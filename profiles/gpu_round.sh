@@ -18,10 +18,10 @@ timeout 300 python profiles/bench_softmax_grad.py 2,2,6 0,32,6 0,128,6 > $out/${
 FSMG_COOP=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv \
     python profiles/profile_step.py 2 > $out/${tag}_launches.log 2>&1
 # --set full captures (one eager step): GEMM-core instantiations of the projection, the recurrent kernels, the softmax-grad pass
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 1 -c 6 -f -o $out/${tag}_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 1 -c 3 -f -o $out/${tag}_gemm \
     python profiles/profile_step.py 1 > $out/${tag}_ncu_gemm.log 2>&1
 FSMG_COOP=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:lstm_ -c 2 -f -o $out/${tag}_lstm \
     python profiles/profile_step.py 1 > $out/${tag}_ncu_lstm.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:softmax_grad -s 2 -c 2 -f -o $out/${tag}_softmax \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:softmax_grad -s 2 -c 1 -f -o $out/${tag}_softmax \
     python profiles/profile_step.py 1 > $out/${tag}_ncu_softmax.log 2>&1
 ls -la $out | grep ${tag}_
