@@ -13,10 +13,10 @@ python profiles/phases.py < $out/${tag}_bench.json
 timeout 300 python bench.py --mode sample --steps 5 --warmup 2 > $out/${tag}_bench_sample.json 2>> $out/${tag}_bench.err
 timeout 300 python bench.py --workload midi5shot_v4708_t256_h1024 --steps 20 --warmup 5 --no-cpu-baseline > $out/${tag}_bench_midi.json 2>> $out/${tag}_bench.err
 timeout 300 python profiles/bench_softmax_grad.py 2,2,6 0,32,6 0,128,6 > $out/${tag}_softmax_grad.log 2>&1
-# launch list of the bench command's hot loop (cold-cache, serialised: shares, not absolutes).  FSMG_COOP=0: ncu cannot replay a
+# launch list of the bench command itself (cold-cache, serialised: shares, not absolutes).  FSMG_COOP=0: ncu cannot replay a
 # cooperative launch that also has a cluster dimension (the pair-mode backward kernel)
-FSMG_COOP=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $out/${tag}_launches.csv \
-    python profiles/profile_step.py 2 > $out/${tag}_launches.log 2>&1
+FSMG_COOP=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file $out/${tag}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_launches.log 2>&1
 # --set full captures (one eager step): GEMM-core instantiations of the projection, the recurrent kernels, the softmax-grad pass
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 1 -c 3 -f -o $out/${tag}_gemm \
     python profiles/profile_step.py 1 > $out/${tag}_ncu_gemm.log 2>&1
