@@ -93,6 +93,7 @@ class Engine:
         self._pinned_scal = torch.empty(8, dtype=torch.float32).pin_memory()
         self._h2d_done: Optional[torch.cuda.Event] = None
         self._ids: Optional[torch.Tensor] = None
+        self._pinned_np = None
 
     # ---- parameters ---------------------------------------------------------------------------
     def param_shapes(self) -> Dict[str, tuple]:
@@ -225,6 +226,37 @@ class Engine:
         self._pinned_scal[:1].copy_(s, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return float(self._pinned_scal[0]) / (float(dev.numel()) + 1e-12)
+
+    def _stage_rows(self, blocks) -> torch.Tensor:
+        """Like _stage for a LIST of [rows, T] arrays (support / query blocks of the step's episodes): every block is copied
+        once, straight into the pinned staging buffer — no intermediate concatenated array on the host."""
+        n = sum(int(b.shape[0]) for b in blocks)
+        if n > self.max_seqs:
+            raise FsmgError(f"{n} sequences > engine capacity {self.max_seqs}")
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        if self._pinned_np is None:
+            self._pinned_np = self._pinned_tok.numpy()      # shares the pinned memory
+        dst = self._pinned_np[: n * self.T].reshape(n, self.T)
+        r = 0
+        for b in blocks:
+            k = int(b.shape[0])
+            if b.shape[1] != self.T:
+                raise FsmgError(f"token rows of length {b.shape[1]} != max_len {self.T}")
+            dst[r:r + k] = b            # numpy casts to int32 on assignment
+            r += k
+        dev = self._tok[: n * self.T]
+        dev.copy_(self._pinned_tok[: n * self.T], non_blocking=True)
+        if self._h2d_done is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+        return dev.view(n, self.T)
+
+    def train_host_rows(self, blocks, global_tokens: Optional[int] = None) -> float:
+        loss = self.train_step_device(self._stage_rows(blocks), global_tokens)
+        self._pinned_scal[:1].copy_(loss, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return float(self._pinned_scal[0])
 
     def train_host(self, tokens: np.ndarray, global_tokens: Optional[int] = None) -> float:
         loss = self.train_step_device(self._stage(tokens), global_tokens)

@@ -105,7 +105,11 @@ class LSTMBaseline(BaseModel):
         if self._indexed(episodes):   # device-resident corpus: only the song indices are uploaded
             loss = self._engine.train_indexed(episodes[0].corpus_device, self._train_ids(episodes))
         else:
-            loss = self._engine.train_host(self._train_tokens(episodes))
+            blocks = []
+            for ep in episodes:     # support rows first, then query rows, per episode (reference :95-96)
+                blocks.append(flatten_first_two_dims(ep.support))
+                blocks.append(flatten_first_two_dims(ep.query))
+            loss = self._engine.train_host_rows(blocks)
         if self._summary_writer:
             self._summary_writer.add_scalar('Train/loss', loss, self._train_calls)
         self._train_calls += 1
