@@ -103,9 +103,15 @@ class EpisodeSampler(object):
     def get_num_unique_words(self):
         return self.dataset.vocab
 
+    detokenizer = None      # set by load_sampler_from_config: MIDI event decoder / lyrics word table when available
+
     def detokenize(self, numpy_data):
-        # no lyrics/MIDI decoder without nltk/pretty_midi: a space-separated id string (write_seq's str branch)
-        return ' '.join(str(int(t)) for t in np.asarray(numpy_data).reshape(-1))
+        """A string for write_seq (reference train.py:17-24): decoded notes for the MIDI vocabulary, words when the corpus
+        ships its word_ids.csv, else the space-separated ids (no .mid writer without pretty_midi)."""
+        ids = np.asarray(numpy_data).reshape(-1)
+        if self.detokenizer is not None:
+            return self.detokenizer(ids)
+        return ' '.join(str(int(t)) for t in ids)
 
 
 def load_sampler_from_config(config):
@@ -138,7 +144,16 @@ def load_sampler_from_config(config):
         raise RuntimeError('split "%s" has %d artists < batch_size %d' % (config['split'], len(corpus), config['batch_size']))
     if config.get('device_episodes', False):   # corpus resident in HBM, episodes are index sets (data/device_episode.py)
         from data.device_episode import DeviceEpisodeSampler
-        return DeviceEpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
-                                    config['max_len'], seed=config.get('seed', None))
-    return EpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
-                          config['max_len'], seed=config.get('seed', None))
+        sampler = DeviceEpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
+                                       config['max_len'], seed=config.get('seed', None))
+    else:
+        sampler = EpisodeSampler(corpus, config['batch_size'], config['support_size'], config['query_size'],
+                                 config['max_len'], seed=config.get('seed', None))
+    if kind in ('midi', 'synthetic_midi') and corpus.vocab == MIDI_VOCAB:
+        from data.midi_events import describe_tokens
+        sampler.detokenizer = describe_tokens
+    elif kind == 'lyrics' and os.path.isfile(os.path.join(config['dataset_path'], 'word_ids.csv')):
+        from data.lyrics_vocab import LyricsVocab
+        vocab = LyricsVocab(os.path.join(config['dataset_path'], 'word_ids.csv'), persist=False)
+        sampler.detokenizer = lambda ids: vocab.detokenize([t for t in ids if int(t) in vocab.id_to_word])
+    return sampler
