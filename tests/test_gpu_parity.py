@@ -244,6 +244,24 @@ def test_train_entry_point_end_to_end(torch_cuda, tmp_path):
     assert "Iter: 6, val-nll" in out.stdout and "Test Avg NLL" in out.stdout
     assert (tmp_path / "ck" / "lstm_baseline" / "lstm_baseline-6.npz").exists()
     assert (tmp_path / "ck" / "samples" / "sample_0" / "model_sample.txt").exists()
+    # the unigram baseline and the MIDI vocabulary (device-resident corpus) through the same entry point
+    data_yaml = tmp_path / "midi.yaml"
+    d = yaml.safe_load(open(PKG / "src" / "config" / "synthetic_midi.yaml"))
+    d.update(max_len=24, synthetic_artists=12, synthetic_songs_per_artist=10, device_episodes=True)
+    yaml.safe_dump(d, open(data_yaml, "w"))
+    for model_cfg in (str(model_yaml), "config/unigram.yaml"):
+        if model_cfg.endswith("unigram.yaml"):
+            u = yaml.safe_load(open(PKG / "src" / model_cfg))
+            u.update(n_train=6, print_every_n=3, val_every_n=3, n_val=2, n_test=2, n_samples=1)
+            model_cfg = str(tmp_path / "unigram.yaml")
+            yaml.safe_dump(u, open(model_cfg, "w"))
+        out = subprocess.run([sys.executable, "-um", "train.train", "--data", str(data_yaml), "--model", model_cfg, "--task",
+                              "config/5shot.yaml", "--checkpt_dir", str(tmp_path / "ck2")],
+                             cwd=str(PKG / "src"), capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "Num unique words: 4708" in out.stdout and "Test Avg NLL" in out.stdout
+        sample = (tmp_path / "ck2" / "samples" / "sample_0" / "model_sample.txt").read_text()
+        assert "family" in sample or "no complete note" in sample          # decoded through data.midi_events
 
 
 def test_sampling_after_training_uses_fresh_weights(torch_cuda):
