@@ -106,7 +106,7 @@ class TorchRef:
                 self.p[k].sub_(alpha * self.m[k] / (self.v[k].sqrt() + 1e-8))
         self.step += 1
         self.last_norm = norm
-        return float(loss)
+        return float(loss.detach())
 
     def params_numpy(self) -> Dict[str, np.ndarray]:
         return {k: v.detach().numpy().copy() for k, v in self.p.items()}
