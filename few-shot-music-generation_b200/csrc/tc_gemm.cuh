@@ -831,115 +831,8 @@ __global__ void __launch_bounds__(256) lse_combine_kernel(const float2* __restri
     }
 }
 
-// in place over the fp16 logits chunk: dlogits = exp(logit - lse) - onehot(y)   (unscaled)
-__global__ void softmax_grad_inplace_kernel(__half* __restrict__ logits, int64_t ld, int vp1, const float* __restrict__ lse,
-                                            const int32_t* __restrict__ y, int64_t row0) {
-    int64_t lr = blockIdx.x;
-    __half* row = logits + lr * ld;
-    const float l = lse[row0 + lr];
-    const int tgt = y[row0 + lr];
-    for (int v = threadIdx.x * 2; v < ld; v += blockDim.x * 2) {
-        __half2 h = *reinterpret_cast<__half2*>(row + v);
-        float2 f = __half22float2(h);
-        float a = v < vp1 ? __expf(f.x - l) - (v == tgt ? 1.0f : 0.0f) : 0.0f;
-        float b = v + 1 < vp1 ? __expf(f.y - l) - (v + 1 == tgt ? 1.0f : 0.0f) : 0.0f;
-        *reinterpret_cast<__half2*>(row + v) = __floats2half2_rn(a, b);
-    }
-}
-
-
-// Fused post-pass over one L2-resident chunk of fp16 logits (training):
-//   (1) combine the per-(row, n-tile) (max, sumexp) partials -> lse ; nll = lse - target logit
-//   (2) in place: dlogits = exp(logit - lse) - onehot(y)            (unscaled, fp16)
-//   (3) db_s += alpha * column sums of dlogits                       (softmax_b gradient)
-// One CTA handles ROWS consecutive rows; each thread owns 8-column groups and keeps their column sums
-// in registers across the CTA's rows, so the bias gradient costs one atomicAdd per column per CTA.
-template <int ROWS, int THREADS, int MAXG>
-__global__ void __launch_bounds__(THREADS) softmax_grad_fused_kernel(__half* __restrict__ logits, int64_t ld, int vp1,
-                                                                      const float2* __restrict__ part, int n_tiles,
-                                                                      const float* __restrict__ tgt, const int32_t* __restrict__ y,
-                                                                      int64_t row0, int rows, int N, int T, float* __restrict__ lse_out,
-                                                                      float* __restrict__ nll_out, float alpha, float* __restrict__ db) {
-    __shared__ float s_lse[ROWS];
-    __shared__ int s_tgt[ROWS];
-    const int r_begin = blockIdx.x * ROWS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int lr = warp; lr < ROWS; lr += THREADS / 32) {
-        const int row = r_begin + lr;
-        if (row >= rows) continue;
-        const float2* p = part + (int64_t)row * n_tiles;
-        float m = -INFINITY;
-        for (int i = lane; i < n_tiles; i += 32) m = fmaxf(m, p[i].x);
-        m = warp_max(m);
-        float s = 0.0f;
-        for (int i = lane; i < n_tiles; i += 32) s += p[i].y * __expf(p[i].x - m);
-        s = warp_sum(s);
-        if (lane == 0) {
-            const float lse = m + logf(s);
-            s_lse[lr] = lse;
-            const int64_t r = row0 + row;
-            s_tgt[lr] = y[r];
-            if (lse_out) lse_out[r] = lse;
-            const int t = (int)(r / N), n = (int)(r % N);
-            if (nll_out) nll_out[(int64_t)n * T + t] = lse - tgt[row];
-        }
-    }
-    __syncthreads();
-    float csum[MAXG][8];
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) csum[g][e] = 0.0f;
-    const int n_rows = min(ROWS, rows - r_begin);
-    constexpr int RB = (MAXG <= 3) ? 4 : 1;   // rows per batch: all loads of a batch are issued before the first exp (memory-level parallelism)
-    for (int lr0 = 0; lr0 < n_rows; lr0 += RB) {
-        uint4 raw[RB][MAXG];
-#pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            const __half* rowp = logits + (int64_t)(r_begin + lr0 + b) * ld;
-#pragma unroll
-            for (int g = 0; g < MAXG; ++g) {
-                const int v0 = (g * THREADS + threadIdx.x) * 8;
-                if (lr0 + b < n_rows && v0 < ld) raw[b][g] = __ldcg(reinterpret_cast<const uint4*>(rowp + v0));
-            }
-        }
-#pragma unroll
-        for (int b = 0; b < RB; ++b) {
-            if (lr0 + b >= n_rows) break;
-            __half* rowp = logits + (int64_t)(r_begin + lr0 + b) * ld;
-            const float lse = s_lse[lr0 + b];
-            const int tg = s_tgt[lr0 + b];
-#pragma unroll
-            for (int g = 0; g < MAXG; ++g) {
-                const int v0 = (g * THREADS + threadIdx.x) * 8;
-                if (v0 < ld) {
-                    __half2* h2 = reinterpret_cast<__half2*>(&raw[b][g]);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float2 f = __half22float2(h2[q]);
-                        const int v = v0 + 2 * q;
-                        float a = v < vp1 ? __expf(f.x - lse) - (v == tg ? 1.0f : 0.0f) : 0.0f;
-                        float bb = v + 1 < vp1 ? __expf(f.y - lse) - (v + 1 == tg ? 1.0f : 0.0f) : 0.0f;
-                        h2[q] = __floats2half2_rn(a, bb);
-                        csum[g][2 * q] += a;
-                        csum[g][2 * q + 1] += bb;
-                    }
-                    *reinterpret_cast<uint4*>(rowp + v0) = raw[b][g];
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g) {
-        const int v0 = (g * THREADS + threadIdx.x) * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-            if (v0 + e < vp1) atomicAdd(db + v0 + e, alpha * csum[g][e]);
-    }
-}
-
-
-// Strip version of the fused post-pass (default): a CTA of 128 threads owns a strip of ROWS rows x 1024 columns; each
+// In-place pass over a chunk of fp16 logits (training): dlogits = exp(logit - lse) - onehot(y) (unscaled, fp16) and
+// db_s += alpha * column sums of dlogits (softmax_b gradient).  Strip version: a CTA of 128 threads owns a strip of ROWS rows x 1024 columns; each
 // thread owns 8 fixed columns and walks down the strip with 8 rows of 16-byte loads in flight, so column sums stay
 // in 8 registers and the kernel needs <= 80 registers and 256 B of smem: it can share an SM with a GEMM CTA.
 template <int ROWS>

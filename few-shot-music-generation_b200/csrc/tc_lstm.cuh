@@ -1184,8 +1184,4 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
     return 0;
 }
 
-// on-device greedy sampler: added in a later milestone
-static inline bool tc_sampler_supported(TcContext&, int, int) { return false; }
-static inline int tc_sample_greedy(TcContext&, int, int, int32_t*, cudaStream_t) { return set_error(-1, "persistent sampler not built"); }
-
 }  // namespace fsmg
