@@ -55,27 +55,56 @@ def make_synthetic_corpus(kind, max_len, vocab, n_artists, songs_per_artist, see
     return TokenCorpus([tok[a] for a in range(n_artists)], vocab, max_len)
 
 
-def load_npy_corpus(root, max_len, min_songs, split, props=(8, 1, 1), seed=0):
+def load_npy_corpus(root, max_len, min_songs, split, props=(8, 1, 1), seed=0, dataset=None):
+    """A corpus tokenised by the reference: ``root/<artist>/<song>.<max_len>.npy`` token caches (base_loader.py:52-64) plus,
+    when present, the metadata directory its Dataset persisted (data/dataset_meta.py).  The reference's data contract is
+    followed: the split comes from ``<split>.csv`` when it exists, else from the reference's own rule (floor counts,
+    ``RandomState(seed).shuffle`` over the artists in ``os.listdir`` order, dataset.py:122-182); ``valid_songs.csv`` filters the
+    songs; the lyrics vocabulary is ``highest word id + 1`` of ``word_ids.csv`` (every word of every song, not just the
+    truncated caches)."""
+    from data.dataset_meta import Metadata, metadata_dir_name, read_valid_songs, read_split, split_artists, highest_word_id, VALID_SONGS_FILE
     suffix = '.%s.npy' % max_len
-    artists = []
-    vocab = 0
-    for artist in sorted(os.listdir(root)):
+    meta = Metadata(root, metadata_dir_name(dataset, max_len), create=False) if dataset else None
+    valid = read_valid_songs(meta) if meta is not None and meta.exists(VALID_SONGS_FILE) else None
+    songs_of, eligible = {}, []
+    for artist in os.listdir(root):                 # listdir order, like the reference (the shuffle below depends on it)
         adir = os.path.join(root, artist)
         if not os.path.isdir(adir):
             continue
-        songs = [np.load(os.path.join(adir, f)).astype(np.int32) for f in sorted(os.listdir(adir)) if f.endswith(suffix)]
-        if len(songs) >= min_songs:
-            artists.append(np.stack(songs))
-            vocab = max(vocab, int(max(s.max() for s in songs)) + 1)
-    if not artists:
-        raise RuntimeError('no artist under %s has >= %d token caches "*%s" (tokenise the corpus with the '
-                           "reference's loaders first: nltk / pretty_midi are not available here)" % (root, min_songs, suffix))
-    order = RandomState(seed).permutation(len(artists))
-    total = float(sum(props))
-    n_train = int(round(len(artists) * props[0] / total))
-    n_val = int(round(len(artists) * props[1] / total))
-    pick = {'train': order[:n_train], 'val': order[n_train:n_train + n_val], 'test': order[n_train + n_val:]}[split]
-    return TokenCorpus([artists[i] for i in pick], vocab, max_len)
+        names = sorted(f[:-len(suffix)] for f in os.listdir(adir) if f.endswith(suffix))
+        if valid is not None:
+            names = [n for n in names if n in valid.get(artist, ())]
+        if names:
+            songs_of[artist] = names
+            if len(names) >= min_songs:
+                eligible.append(artist)
+    persisted = read_split(meta, split) if meta is not None else None
+    if persisted is not None:
+        missing = [a for a in persisted if a not in songs_of]
+        if missing:
+            raise RuntimeError('%d artists of the persisted %s split have no token caches "*%s" under %s (first: %r)'
+                               % (len(missing), split, suffix, root, missing[0]))
+        chosen = persisted
+    else:
+        chosen = split_artists(eligible, props, seed)[split]
+    if not chosen:
+        raise RuntimeError('no artist under %s has >= %d token caches "*%s" for the %s split (tokenise the corpus with the '
+                           "reference's loaders first: nltk / pretty_midi are not available here)" % (root, min_songs, suffix, split))
+    artists, vocab = [], 0
+    for artist in chosen:
+        songs = [np.load(os.path.join(root, artist, n + suffix)).astype(np.int32) for n in songs_of[artist]]
+        artists.append(np.stack(songs))
+        vocab = max(vocab, int(max(s.max() for s in songs)) + 1)
+    corpus = TokenCorpus(artists, vocab, max_len)
+    corpus.artist_names = list(chosen)
+    corpus.word_ids_path = None
+    for cand in ((meta.path('word_ids.csv') if meta is not None else None), os.path.join(root, 'word_ids.csv')):
+        if cand and os.path.isfile(cand):
+            corpus.word_ids_path = cand
+            break
+    if meta is not None and meta.exists('word_ids.csv'):
+        corpus.vocab = highest_word_id(meta) + 1     # LyricsLoader.get_num_tokens (lyrics_loader.py:63-64)
+    return corpus
 
 
 class EpisodeSampler(object):
@@ -135,7 +164,7 @@ def load_sampler_from_config(config):
         if not os.path.isdir(root):
             raise RuntimeError('required data directory %s does not exist' % root)
         props = (config.get('train_proportion', 8), config.get('val_proportion', 1), config.get('test_proportion', 1))
-        corpus = load_npy_corpus(root, config['max_len'], min_songs, config['split'], props, config.get('dataset_seed', 0))
+        corpus = load_npy_corpus(root, config['max_len'], min_songs, config['split'], props, config.get('dataset_seed', 0), dataset=kind)
         if kind == 'midi':
             corpus.vocab = MIDI_VOCAB
     else:
@@ -152,8 +181,8 @@ def load_sampler_from_config(config):
     if kind in ('midi', 'synthetic_midi') and corpus.vocab == MIDI_VOCAB:
         from data.midi_events import describe_tokens
         sampler.detokenizer = describe_tokens
-    elif kind == 'lyrics' and os.path.isfile(os.path.join(config['dataset_path'], 'word_ids.csv')):
+    elif kind == 'lyrics' and getattr(corpus, 'word_ids_path', None):
         from data.lyrics_vocab import LyricsVocab
-        vocab = LyricsVocab(os.path.join(config['dataset_path'], 'word_ids.csv'), persist=False)
+        vocab = LyricsVocab(corpus.word_ids_path, persist=False)
         sampler.detokenizer = lambda ids: vocab.detokenize([t for t in ids if int(t) in vocab.id_to_word])
     return sampler
