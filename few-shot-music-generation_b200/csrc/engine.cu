@@ -159,7 +159,7 @@ struct Bump {
 static void carve(fsmg_handle* h, char* base) {
     Bump b{base};
     const int64_t NT = (int64_t)h->Nmax * h->T;
-    h->scalars = b.take<float>(64);
+    h->scalars = b.take<float>(512);   // [0..7] results, [32] token-range error count (int), [64..64+SQNORM_BLOCKS) norm partials
     h->x_ids = b.take<int32_t>(NT);
     h->y_ids = b.take<int32_t>(NT);
     h->tok_stage = b.take<int32_t>(NT);
@@ -323,7 +323,8 @@ static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, bool tra
     const int64_t NT = (int64_t)N * T;
     {
     ProfScope ps(h, PH_PREP, s);
-    prep_tokens_kernel<<<cdiv(NT, TB), TB, 0, s>>>(d_tokens, h->x_ids, h->y_ids, N, T, h->V, h->V);
+    prep_tokens_kernel<<<cdiv(NT, TB), TB, 0, s>>>(d_tokens, h->x_ids, h->y_ids, N, T, h->V, h->V, reinterpret_cast<int*>(h->scalars + 32),
+                                                   train && h->grads ? h->grads + h->n_params + 2 : nullptr);
     LAUNCH_COUNT(h);
         // the gathered embedding rows are only needed by the per-token input GEMM (forward) / weight-gradient GEMM (backward)
         if (!layer0_word_forward(h, N) || (train && !layer0_word_backward(h, N))) {
@@ -788,6 +789,10 @@ int fsmg_create(const fsmg_config* cfg, const char* scope_name, fsmg_handle** ou
     if (cfg->vocab <= 0 || cfg->embed <= 0 || cfg->hidden <= 0 || cfg->layers <= 0 || cfg->max_len <= 0 || cfg->max_seqs <= 0)
         return set_error(FSMG_ERR_INVALID, "non-positive dimension in fsmg_config");
     if (cfg->max_len > 4096) return set_error(FSMG_ERR_INVALID, "max_len > 4096 unsupported");
+    // several kernels put the token count / 64 in gridDim.y (limit 65535) and index tokens with 32-bit ints
+    if ((int64_t)cfg->max_len * cfg->max_seqs > (int64_t)65535 * 64)
+        return set_error(FSMG_ERR_INVALID, "max_seqs * max_len = %lld tokens per call exceeds the supported %lld", (long long)cfg->max_len * cfg->max_seqs,
+                         (long long)65535 * 64);
     fsmg_handle* h = new fsmg_handle();
     h->cfg = *cfg;
     h->scope = scope_name && *scope_name ? scope_name : "lstm_baseline";
@@ -901,6 +906,7 @@ int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, 
     if (h->samp_graph_multi) { cudaGraphExecDestroy(h->samp_graph_multi); h->samp_graph_multi = nullptr; }
     h->samp_stale = true;
     h->bound = true;
+    FSMG_CUDA_OK(cudaMemset(h->scalars, 0, 512 * sizeof(float)));
     return FSMG_OK;
 }
 
@@ -997,10 +1003,9 @@ int fsmg_apply_update(fsmg_handle* h, int64_t step, float* d_out_norm, void* str
     float lr_k = h->cfg.lr * powf(0.5f, (float)step / (float)h->cfg.n_decay);
     double t = (double)step + 1.0;
     double alpha = (double)lr_k * sqrt(1.0 - pow((double)h->cfg.beta2, t)) / (1.0 - pow((double)h->cfg.beta1, t));
-    float* dense_sq = h->scalars + 8;
+    float* dense_sq = h->scalars + 64;   // SQNORM_BLOCKS per-block partials, combined in a fixed order by clip_adam_kernel
     ProfScope ps(h, PH_UPDATE, s);
-    FSMG_CUDA_OK(cudaMemsetAsync(dense_sq, 0, sizeof(float), s));
-    sqnorm_f32_kernel<<<296, 256, 0, s>>>(h->grads, h->dense_begin, h->n_params, dense_sq);
+    sqnorm_f32_kernel<<<SQNORM_BLOCKS, 256, 0, s>>>(h->grads, h->dense_begin, h->n_params, dense_sq);
     clip_adam_kernel<<<592, 256, 0, s>>>(h->params, h->grads, h->adam_m, h->adam_v, h->n_params, dense_sq,
                                          h->grads + h->n_params + 1, h->cfg.max_grad_norm, (float)alpha, h->cfg.beta1,
                                          h->cfg.beta2, h->cfg.eps, d_out_norm);
@@ -1048,6 +1053,15 @@ int fsmg_sample_greedy(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------
+// TensorFlow raises InvalidArgument for an id outside the embedding table (reference lstm_baseline.py:41, tf.nn.embedding_lookup)
+static int check_host_tokens(const fsmg_handle* h, const int32_t* tok, int64_t n) {
+    if (!tok) return set_error(FSMG_ERR_INVALID, "null token buffer");
+    for (int64_t i = 0; i < n; ++i)
+        if (tok[i] < 0 || tok[i] > h->V)
+            return set_error(FSMG_ERR_INVALID, "token id %d at flat index %lld outside [0, %d] (input_size = %d)", tok[i], (long long)i, h->V, h->V);
+    return FSMG_OK;
+}
+
 static int ensure_host_staging(fsmg_handle* h, int64_t tok_elems) {
     if (!h->h_scal) FSMG_CUDA_OK(cudaHostAlloc((void**)&h->h_scal, 64 * sizeof(float), cudaHostAllocDefault));
     if (tok_elems > h->h_tok_elems) {
@@ -1064,6 +1078,8 @@ int fsmg_eval_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, floa
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     int64_t n = (int64_t)n_seqs * h->T;
+    rc = check_host_tokens(h, h_tokens, n);
+    if (rc) return rc;
     rc = ensure_host_staging(h, (int64_t)h->Nmax * h->T);
     if (rc) return rc;
     memcpy(h->h_tok, h_tokens, n * sizeof(int32_t));
@@ -1082,6 +1098,8 @@ int fsmg_train_host(fsmg_handle* h, const int32_t* h_tokens, int32_t n_seqs, int
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     int64_t n = (int64_t)n_seqs * h->T;
+    rc = check_host_tokens(h, h_tokens, n);
+    if (rc) return rc;
     rc = ensure_host_staging(h, (int64_t)h->Nmax * h->T);
     if (rc) return rc;
     memcpy(h->h_tok, h_tokens, n * sizeof(int32_t));
@@ -1105,6 +1123,29 @@ int fsmg_sample_host(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t*
     if (rc) return rc;
     FSMG_CUDA_OK(cudaMemcpyAsync(h_out, h->samp_out2, (int64_t)n_songs * n_tokens * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     FSMG_CUDA_OK(cudaStreamSynchronize(s));
+    return FSMG_OK;
+}
+
+// device-pointer callers: how many token ids of the calls so far were outside [0, V] (they were clamped); resets the count
+int fsmg_token_range_errors(fsmg_handle* h, int64_t* h_count, void* stream) {
+    if (!h || !h->bound || !h_count) return set_error(FSMG_ERR_STATE, "not bound / null argument");
+    int v = 0;
+    FSMG_CUDA_OK(cudaMemcpyAsync(&v, h->scalars + 32, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    FSMG_CUDA_OK(cudaMemsetAsync(h->scalars + 32, 0, sizeof(int), (cudaStream_t)stream));
+    FSMG_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    *h_count = v;
+    return FSMG_OK;
+}
+
+// the device-side input/target shift on its own (parity hook for base_model.py:63-86): time-major x / y ids of a token batch
+int fsmg_debug_prep_tokens(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, int32_t* d_x_out, int32_t* d_y_out, void* stream) {
+    int rc = check_call(h, n_seqs);
+    if (rc) return rc;
+    if (!d_tokens || !d_x_out || !d_y_out) return set_error(FSMG_ERR_INVALID, "null argument");
+    const int64_t NT = (int64_t)n_seqs * h->T;
+    prep_tokens_kernel<<<cdiv(NT, 256), 256, 0, (cudaStream_t)stream>>>(d_tokens, d_x_out, d_y_out, n_seqs, h->T, h->V, h->V,
+                                                                          reinterpret_cast<int*>(h->scalars + 32));
+    FSMG_LAUNCH_OK();
     return FSMG_OK;
 }
 

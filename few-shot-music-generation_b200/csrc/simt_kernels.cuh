@@ -114,13 +114,17 @@ static inline void launch_simt_gemm(const GemmArgs& g, bool a_mn, bool b_mn, cud
 // device, re-ordered time-major: r = t*N + n.   x[r] = t ? tok[n,t-1] : V ;  y[r] = tok[n,t]
 // ============================================================================================
 __global__ void prep_tokens_kernel(const int32_t* __restrict__ tok, int32_t* __restrict__ x,
-                                   int32_t* __restrict__ y, int N, int T, int start_word, int vmax) {
+                                   int32_t* __restrict__ y, int N, int T, int start_word, int vmax, int* __restrict__ range_errors,
+                                   float* __restrict__ token_count = nullptr) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= (int64_t)N * T) return;
+    if (r == 0 && token_count) *token_count = (float)((int64_t)N * T);   // piggy-backed on the gradient all-reduce (FSMG_GRAD_EXTRA slot 2)
     int t = (int)(r / N), n = (int)(r % N);
     int cur = tok[(int64_t)n * T + t];
     int prev = t ? tok[(int64_t)n * T + t - 1] : start_word;
-    // ids outside [0, V] would index out of the tables: clamp (the reference would raise in TF)
+    // ids outside [0, V] would index out of the tables (TensorFlow raises InvalidArgument): count them in a device flag the
+    // host entry points turn into an error, and clamp so that the step itself stays memory-safe
+    if ((cur < 0 || cur > vmax) && range_errors) atomicAdd(range_errors, 1);
     cur = min(max(cur, 0), vmax);
     prev = min(max(prev, 0), vmax);
     x[r] = prev;
@@ -314,8 +318,12 @@ __global__ void sum_f32_kernel(const float* __restrict__ x, int64_t n, float* __
     if (threadIdx.x == 0) atomicAdd(out, s);
 }
 
-// sum of squares over [begin, end) of a float array -> atomicAdd (double accumulation per thread)
-__global__ void sqnorm_f32_kernel(const float* __restrict__ x, int64_t begin, int64_t end, float* __restrict__ out) {
+// sum of squares over [begin, end) of a float array, ORDER-DETERMINISTIC: every block writes its partial (fixed grid-stride order,
+// fixed shuffle tree) to partials[blockIdx.x]; clip_adam_kernel adds the partials in a fixed order.  Data-parallel replicas hold
+// bit-identical all-reduced gradients, so they derive bit-identical clip factors and never drift apart (an atomicAdd combine
+// differed by an ulp between ranks).
+constexpr int SQNORM_BLOCKS = 296;
+__global__ void sqnorm_f32_kernel(const float* __restrict__ x, int64_t begin, int64_t end, float* __restrict__ partials) {
     __shared__ float red[32];
     float s = 0.0f;
     for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < end; i += (int64_t)gridDim.x * blockDim.x) {
@@ -323,7 +331,16 @@ __global__ void sqnorm_f32_kernel(const float* __restrict__ x, int64_t begin, in
         s = fmaf(v, v, s);
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+// fixed-order sum of the SQNORM_BLOCKS partials by one warp, in double (same result in every block, on every rank)
+__device__ __forceinline__ float sqnorm_combine(const float* __restrict__ partials) {
+    double acc = 0.0;
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < SQNORM_BLOCKS; i += 32) acc += (double)partials[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return (float)acc;
 }
 
 // ============================================================================================
@@ -336,7 +353,14 @@ __global__ void clip_adam_kernel(float* __restrict__ p, const float* __restrict_
                                  float* __restrict__ v, int64_t n, const float* __restrict__ dense_sq,
                                  const float* __restrict__ occ_sq, float clip, float alpha_t, float beta1,
                                  float beta2, float eps, float* __restrict__ norm_out) {
-    float norm = sqrtf(*dense_sq + *occ_sq);
+    // dense_sq: SQNORM_BLOCKS per-block partials of sqnorm_f32_kernel, combined here in a fixed order
+    __shared__ float dense_total;
+    if (threadIdx.x < 32) {
+        const float t = sqnorm_combine(dense_sq);
+        if (threadIdx.x == 0) dense_total = t;
+    }
+    __syncthreads();
+    float norm = sqrtf(dense_total + *occ_sq);
     float scale = clip / fmaxf(norm, clip);
     if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
     auto upd = [&](float& pi, float gi_raw, float& mi, float& vi) {

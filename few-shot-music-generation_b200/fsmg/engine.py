@@ -94,6 +94,7 @@ class Engine:
         self._h2d_done: Optional[torch.cuda.Event] = None
         self._ids: Optional[torch.Tensor] = None
         self._pinned_np = None
+        self._checked_corpora = set()
 
     # ---- parameters ---------------------------------------------------------------------------
     def param_shapes(self) -> Dict[str, tuple]:
@@ -167,7 +168,21 @@ class Engine:
             torch.distributed.all_reduce(self.grads, group=self.pg)
         _lib.check(self.lib.fsmg_apply_update(self.h, self.global_step, 0, self._stream()))
         self.global_step += 1
+        self._last_gt = float(gt)
+        self._last_gt_assumed = global_tokens is None
         return self.grads[self.n_params: self.n_params + 1] / (float(gt) + 1e-12)
+
+    def _read_loss(self) -> float:
+        """D2H of the step's scalars (sum of NLL, token count) after train_step_device: the mean loss of the global batch.  The
+        all-reduced token count (grads[n_params + 2], written by the library) must equal the count the loss scale assumed —
+        unequal shards across ranks would otherwise train with a silently wrong gradient scale."""
+        self._pinned_scal[:4].copy_(self.grads[self.n_params: self.n_params + 4], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        total, count = float(self._pinned_scal[0]), float(self._pinned_scal[2])
+        if self._last_gt_assumed and abs(count - self._last_gt) > 1e-6 * self._last_gt:
+            raise FsmgError(f"ranks processed {count:.0f} tokens in this step but the loss was scaled for {self._last_gt:.0f}: "
+                            "every rank must hold the same number of sequences, or pass global_tokens explicitly")
+        return total / (self._last_gt + 1e-12)
 
     def sample_greedy_device(self, n_songs: int, n_tokens: int) -> torch.Tensor:
         out = torch.empty((n_songs, n_tokens), dtype=torch.int32, device=self.device)
@@ -175,11 +190,18 @@ class Engine:
         return out
 
     # ---- host-buffer entry points (numpy in, python scalars out: what LSTMBaseline uses) -------------
+    def _check_ids(self, tok: np.ndarray) -> None:
+        """TensorFlow's embedding_lookup raises for ids outside the table (reference lstm_baseline.py:41); so do we —
+        a vocabulary / input_size mismatch must not train on clamped garbage."""
+        if tok.size and (int(tok.min()) < 0 or int(tok.max()) > self.V):
+            raise FsmgError(f"token ids span [{int(tok.min())}, {int(tok.max())}], outside [0, {self.V}] (input_size = {self.V})")
+
     def _stage(self, tokens: np.ndarray) -> torch.Tensor:
         tok = np.ascontiguousarray(tokens, dtype=np.int32).reshape(-1, self.T)
         n = tok.shape[0]
         if n > self.max_seqs:
             raise FsmgError(f"{n} sequences > engine capacity {self.max_seqs}")
+        self._check_ids(tok)
         if self._h2d_done is not None:
             self._h2d_done.synchronize()      # the previous asynchronous H2D copy has finished reading the pinned buffer
         self._pinned_tok[: n * self.T].copy_(torch.from_numpy(tok.reshape(-1)))
@@ -200,6 +222,12 @@ class Engine:
         assert corpus.dtype == torch.int32 and corpus.is_cuda and corpus.is_contiguous() and corpus.shape[1] == self.T
         if n and (ids.min() < 0 or ids.max() >= corpus.shape[0]):
             raise FsmgError("song index outside the corpus")
+        key = (corpus.data_ptr(), tuple(corpus.shape))
+        if key not in self._checked_corpora:      # one device reduction per corpus, at its first use
+            lo, hi = int(corpus.min()), int(corpus.max())
+            if lo < 0 or hi > self.V:
+                raise FsmgError(f"corpus token ids span [{lo}, {hi}], outside [0, {self.V}] (input_size = {self.V})")
+            self._checked_corpora.add(key)
         if self._h2d_done is not None:
             self._h2d_done.synchronize()
         if self._ids is None:
@@ -215,10 +243,8 @@ class Engine:
         return dev.view(n, self.T)
 
     def train_indexed(self, corpus: torch.Tensor, row_ids: np.ndarray, global_tokens: Optional[int] = None) -> float:
-        loss = self.train_step_device(self._stage_indexed(corpus, row_ids), global_tokens)
-        self._pinned_scal[:1].copy_(loss, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return float(self._pinned_scal[0])
+        self.train_step_device(self._stage_indexed(corpus, row_ids), global_tokens)
+        return self._read_loss()
 
     def eval_indexed(self, corpus: torch.Tensor, row_ids: np.ndarray) -> float:
         dev = self._stage_indexed(corpus, row_ids)
@@ -245,6 +271,7 @@ class Engine:
                 raise FsmgError(f"token rows of length {b.shape[1]} != max_len {self.T}")
             dst[r:r + k] = b            # numpy casts to int32 on assignment
             r += k
+        self._check_ids(dst)
         dev = self._tok[: n * self.T]
         dev.copy_(self._pinned_tok[: n * self.T], non_blocking=True)
         if self._h2d_done is None:
@@ -253,16 +280,12 @@ class Engine:
         return dev.view(n, self.T)
 
     def train_host_rows(self, blocks, global_tokens: Optional[int] = None) -> float:
-        loss = self.train_step_device(self._stage_rows(blocks), global_tokens)
-        self._pinned_scal[:1].copy_(loss, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return float(self._pinned_scal[0])
+        self.train_step_device(self._stage_rows(blocks), global_tokens)
+        return self._read_loss()
 
     def train_host(self, tokens: np.ndarray, global_tokens: Optional[int] = None) -> float:
-        loss = self.train_step_device(self._stage(tokens), global_tokens)
-        self._pinned_scal[:1].copy_(loss, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        return float(self._pinned_scal[0])
+        self.train_step_device(self._stage(tokens), global_tokens)
+        return self._read_loss()
 
     def eval_host(self, tokens: np.ndarray, return_nll: bool = False):
         dev = self._stage(tokens)

@@ -210,10 +210,16 @@ class LSTMBaseline(BaseModel):
         return True
 
     def recover_or_init(self, init_path, only_load_trainable_vars=False):
-        """Initialise every variable (Glorot-uniform from config['seed'], A.1), then overwrite what a
-        checkpoint under init_path provides — same end state as restore + init-uninitialised."""
-        self._engine.init_params(int(self._seed))
-        self._initialized = True
+        """Restore what a checkpoint under init_path provides and initialise the rest (reference tf_model.py:112-129: restore,
+        then run the initialiser of the variables that are STILL uninitialised).  On a fresh model every variable is first
+        drawn Glorot-uniform from config['seed'] (A.1) with zero Adam slots and global_step 0; on a model that already holds
+        weights (trained, or restored before) nothing is re-drawn — only the checkpoint, if any, is applied."""
+        if not self._initialized:
+            self._engine.init_params(int(self._seed))
+            self._engine.adam_m.zero_()
+            self._engine.adam_v.zero_()
+            self._engine.global_step = 0
+            self._initialized = True
         self._recover(init_path, only_load_trainable_vars)
 
     # ---- test / parity hooks ----------------------------------------------------------------------

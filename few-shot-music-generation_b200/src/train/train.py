@@ -33,12 +33,37 @@ def write_seq(seq, dir, name):
         seq.write(os.path.join(dir, name + '.mid'))
 
 
-def evaluate(model, episode_sampler, n_episodes):
-    """Mean of per-episode mean NLLs (reference :27-33)."""
-    avg_nll = 0.
-    for _ in range(n_episodes):
-        avg_nll += model.eval(episode_sampler.get_episode())
-    return avg_nll / n_episodes
+def evaluate(model, episode_sampler, n_episodes, rank=0, world=1, shared_stream=True):
+    """Mean of per-episode mean NLLs (reference :27-33).
+
+    Under torchrun the n_episodes of ONE evaluation are sharded over the ranks and the sum is all-reduced, so an N-GPU run
+    reports the number the reference's loop would.  With `shared_stream` (val / test samplers: same seed on every rank) every
+    rank draws all n_episodes from the identical sampler stream and scores episodes i = rank (mod world): exactly the
+    episodes of the single-process evaluation.  Without it (the train sampler, seeded per rank) each rank scores its share
+    of episodes from its own stream."""
+    if world <= 1:
+        avg_nll = 0.
+        for _ in range(n_episodes):
+            avg_nll += model.eval(episode_sampler.get_episode())
+        return avg_nll / n_episodes
+    total = 0.
+    for i in range(n_episodes):
+        if shared_stream:
+            episode = episode_sampler.get_episode()        # keeps the stream aligned across ranks
+            if i % world == rank:
+                total += model.eval(episode)
+        elif i % world == rank:
+            total += model.eval(episode_sampler.get_episode())
+    return all_reduce_sum(total) / n_episodes
+
+
+def all_reduce_sum(value):
+    import torch
+    import torch.distributed as dist
+    device = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t)
+    return float(t[0])
 
 
 def build_parser():
@@ -85,8 +110,10 @@ def main(argv=None):
     base_seed = config.get('seed', None)
     for split in config['splits']:
         config['split'] = split
-        if base_seed is not None and world > 1:  # every rank draws its own episodes
-            config['seed'] = base_seed + rank
+        if base_seed is not None and world > 1 and split == 'train':   # every rank trains on its own episodes;
+            config['seed'] = base_seed + rank                            # val / test keep ONE stream (sharded in evaluate)
+        elif base_seed is not None:
+            config['seed'] = base_seed
         episode_sampler[split] = load_sampler_from_config(config)
     if base_seed is not None:
         config['seed'] = base_seed  # identical initial weights on every rank
@@ -103,7 +130,8 @@ def main(argv=None):
     model = load_model_from_config(config)
     model.recover_or_init(args.init_dir)
 
-    avg_nll = evaluate(model, episode_sampler['val'], n_val)
+    shared = base_seed is not None      # unseeded samplers (np.random) cannot be aligned across ranks
+    avg_nll = evaluate(model, episode_sampler['val'], n_val, rank, world, shared)
     log('Iter: %d, val-nll: %.3e' % (0, avg_nll))
 
     avg_loss = 0.
@@ -114,7 +142,7 @@ def main(argv=None):
             loss = model.train([episode_sampler['train'].get_episode() for _ in range(per_step)])
         avg_loss += loss
         if i % val_every_n == 0:
-            avg_nll = evaluate(model, episode_sampler['val'], n_val)
+            avg_nll = evaluate(model, episode_sampler['val'], n_val, rank, world, shared)
             log('Iter: %d, val-nll: %.3e' % (i, avg_nll))
             if args.checkpt_dir != '':
                 model.save(args.checkpt_dir)
@@ -123,10 +151,17 @@ def main(argv=None):
             avg_loss = 0.
 
     for split, label in (('train', 'Train'), ('val', 'Validation'), ('test', 'Test')):
-        log('%s Avg NLL: %.3e' % (label, evaluate(model, episode_sampler[split], n_test)))
+        log('%s Avg NLL: %.3e' % (label, evaluate(model, episode_sampler[split], n_test, rank, world, shared and split != 'train')))
 
-    if rank != 0:
-        return
+    if rank == 0:
+        write_samples(model, episode_sampler, args, n_samples, max_len)
+    if world > 1:       # nobody leaves (and tears the process group down) while rank 0 is still sampling
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def write_samples(model, episode_sampler, args, n_samples, max_len):
     samples_dir = os.path.join(args.checkpt_dir, 'samples')
     os.makedirs(samples_dir, exist_ok=True)
     for i in range(n_samples):

@@ -90,7 +90,8 @@ void fsmg_destroy(fsmg_handle* h);
 
 /* Sizes the caller must allocate: flat parameter count (padded), gradient buffer count
  * (= params + FSMG_GRAD_EXTRA scalar slots), workspace bytes. */
-#define FSMG_GRAD_EXTRA 8  /* [0]=sum of per-token NLL, [1]=per-occurrence embedding-grad square norm (TF clip quirk) */
+#define FSMG_GRAD_EXTRA 8  /* [0]=sum of per-token NLL, [1]=per-occurrence embedding-grad square norm (TF clip quirk),
+                              [2]=tokens in this call (summed by the data-parallel all-reduce: the global token count) */
 int64_t fsmg_param_count(const fsmg_handle* h);
 int64_t fsmg_grad_count(const fsmg_handle* h);
 int64_t fsmg_workspace_bytes(const fsmg_handle* h);
@@ -144,6 +145,18 @@ int fsmg_sample_host(fsmg_handle* h, int32_t n_songs, int32_t n_tokens, int32_t*
 int fsmg_set_profile(fsmg_handle* h, int enable);
 int fsmg_read_profile(fsmg_handle* h, float* ms_out, int32_t* count_out, void* stream);
 const char* fsmg_profile_phase_name(int phase);
+
+/* Token ids outside [0, V] (TensorFlow's embedding_lookup raises InvalidArgument for them, lstm_baseline.py:41): the
+ * host entry points reject them with FSMG_ERR_INVALID before anything is copied; the device-pointer entry points clamp
+ * them (memory safety) and count them in a device flag.  fsmg_token_range_errors synchronises the stream, returns the
+ * count accumulated since the last query and resets it. */
+int fsmg_token_range_errors(fsmg_handle* h, int64_t* h_count, void* stream);
+
+/* The device-side input/target shift on its own — convert_tokens_to_input_and_target with start word V
+ * (reference src/models/base_model.py:63-86) — for parity tests: d_tokens [n_seqs, T] -> d_x_out, d_y_out, both
+ * TIME-MAJOR [T, n_seqs] (element t*n_seqs + n), the layout every kernel of the path reads. */
+int fsmg_debug_prep_tokens(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs, int32_t* d_x_out, int32_t* d_y_out,
+                           void* stream);
 
 /* Introspection for benchmarks/tests: number of kernel launches issued by the last call,
  * and a GEMM self-test entry (C[M,N] = A[M,K] * B[N,K]^T, fp16 in, fp32 out) that drives the

@@ -212,6 +212,53 @@ def test_data_parallel_protocol_world2_gloo(tmp_path):
     assert "DP_OK" in outs[0]
 
 
+EVAL_WORKER = r'''
+import os, sys, numpy as np, torch.distributed as dist
+for p in os.environ["FSMG_PATHS"].split(os.pathsep):
+    sys.path.insert(0, p)
+from data.episode import load_sampler_from_config
+from train.train import evaluate
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"], rank=rank, world_size=2)
+cfg = dict(dataset="synthetic_lyrics", dataset_path=".", split="val", batch_size=5, support_size=5, query_size=4, max_len=8,
+           synthetic_vocab=300, synthetic_artists=12, synthetic_songs_per_artist=11, seed=4)
+class Model:
+    def __init__(self): self.seen = []
+    def eval(self, ep):
+        self.seen.append(int(ep.query.sum()))
+        return float(ep.query.sum() % 1009) / 7.0
+m = Model()
+got = evaluate(m, load_sampler_from_config(dict(cfg)), 9, rank, 2, True)
+assert len(m.seen) == (5 if rank == 0 else 4)          # 9 episodes sharded 5 + 4, each scored exactly once
+single = Model()
+want = evaluate(single, load_sampler_from_config(dict(cfg)), 9)
+assert m.seen == single.seen[rank::2]                   # the SAME episodes the single-process loop scores
+assert abs(got - want) < 1e-12, (got, want)
+own = evaluate(Model(), load_sampler_from_config(dict(cfg, seed=4 + rank)), 9, rank, 2, False)   # per-rank streams: still 9 episodes in total
+assert np.isfinite(own)
+if rank == 0:
+    print("EVAL_OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_evaluate_equals_the_single_process_loop_world2_gloo(tmp_path):
+    """train.evaluate under torchrun (reference src/train/train.py:27-33): the episodes of one evaluation are sharded over the
+    ranks of a world_size-2 gloo group and the all-reduced mean equals the reference loop over the same sampler stream."""
+    script = tmp_path / "eval_worker.py"
+    script.write_text(EVAL_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=port, OMP_NUM_THREADS="1",
+                   FSMG_PATHS=os.pathsep.join([str(ROOT), str(PKG), str(PKG / "src")]))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "EVAL_OK" in outs[0]
+
+
 def test_package_synthetic_generator_matches_oracle_generator():
     """bench.py's product arm draws its episodes from data.synthetic (no oracle import); the tests draw theirs
     from the oracle.  Same seed -> same episodes, so parity runs and bench runs see identical inputs."""

@@ -1,6 +1,7 @@
-"""GPU tests at BASELINE.json's FULL sizes.  The fp64/fp32 oracle cannot run 1440 x 128 tokens with a 10k vocabulary in
-seconds, so parity at full size rests on (a) the oracle (torch-CPU fp32 restatement, oracle/torch_ref.py) on ONE episode
-at the full model dimensions and (b) size-independent properties of the path that tie the full batch to that episode:
+"""GPU tests at BASELINE.json's FULL sizes.  The per-token NLL of the complete 1440 x 128 batch of configs[1] is compared with
+the fp32 oracle (torch-CPU restatement, oracle/torch_ref.py, forward only, a few seconds per 90 sequences); the training
+step at full size rests on (a) the oracle on ONE episode at the full model dimensions and (b) size-independent properties
+of the path that tie the full batch to that episode:
 
 * sequences are independent (reference lstm_baseline.py:50-55: zero initial state per row): the NLL of an episode's
   rows does not depend on what else is in the batch;
@@ -58,6 +59,29 @@ def test_cfg1_full_batch_nll_rows_independent_and_match_oracle_episode(torch_cud
     perm = np.random.RandomState(5).permutation(n)
     _, nll_perm = eng.eval_host(tok[perm], return_nll=True)
     assert np.max(np.abs(nll_perm - nll_full[perm]) / nll_full[perm]) < 1e-5
+    eng.close()
+
+
+def test_cfg1_full_batch_per_token_nll_matches_fp32_oracle_on_every_row(torch_cuda):
+    """All 184 320 tokens of the configs[1] batch (32 episodes x 45 sequences x 128, V=10k, E=H=512): per-token NLL within
+    1e-3 relative of the fp32 reference path (BASELINE.json north_star), no sampling of rows."""
+    from fsmg.engine import Engine
+    from oracle.torch_ref import TorchRef
+    torch = torch_cuda
+    cfg = _cfg(10000, 512, 512, 128)
+    n = 32 * EPISODE
+    params = O.glorot_init(cfg, 1234)
+    tok = O.synthetic_tokens(np.random.RandomState(21), (n, 128), 10000, "zipf")
+    tok[5, 40:] = 0                                  # a zero-padded sequence: pad id 0 is scored (base_loader.py:59-61)
+    eng = Engine(cfg, max_seqs=n, device="cuda:0")
+    eng.load_params(params)
+    _, nll = eng.eval_host(tok, return_nll=True)
+    ref = TorchRef(params, cfg, torch.float32)
+    worst = 0.0
+    for r0 in range(0, n, 2 * EPISODE):              # the oracle in slices (fp32 logits of a slice: 460 MB)
+        want = ref.per_token_nll(tok[r0:r0 + 2 * EPISODE])
+        worst = max(worst, float(np.max(np.abs(nll[r0:r0 + 2 * EPISODE] - want) / want)))
+    assert worst < 1e-3, worst
     eng.close()
 
 
@@ -150,9 +174,6 @@ def test_cfg4_full_size_greedy_generation_is_identical_across_songs_and_matches_
     out = eng.sample_host(256, 512)
     assert out.shape == (256, 512) and out.min() >= 0 and out.max() <= 4708
     assert (out == out[0:1]).all()             # zero state + start word + argmax: every song is the same sequence
-    want, margins = O.sample_greedy(params, 512, np.float64, True)
-    for i, (a, b) in enumerate(zip(out[0].tolist(), want)):
-        if a != b:
-            assert margins[i] < 1e-6, (i, a, b, margins[i])    # a numerical tie in the fp64 oracle itself
-            break
+    from test_gpu_parity import assert_greedy
+    assert_greedy(params, out[0], O.sample_greedy(params, 512, np.float64))   # all 512 tokens, teacher-forced past any tie
     eng.close()

@@ -37,6 +37,21 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)))
 
 
+def assert_greedy(params, got, want=None):
+    """Token indices bit-exact: EVERY generated token must be the fp64 oracle's argmax for the sequence generated so far
+    (teacher-forced, so the check does not stop at the first numerical tie); a token other than the argmax is accepted only
+    when the oracle's own logits put it within TIE_MARGIN of the maximum.  Up to the first such tie the sequence must equal
+    the oracle's free-running decode `want`."""
+    got = [int(t) for t in got]
+    deficit = O.greedy_deficits(params, got, np.float64)
+    bad = np.nonzero(deficit >= TIE_MARGIN)[0]
+    assert bad.size == 0, f"token {bad[0]} = {got[bad[0]]} is {deficit[bad[0]]:.3e} below the oracle's maximum logit"
+    if want is not None:
+        ties = np.nonzero(deficit > 0)[0]
+        upto = int(ties[0]) if ties.size else len(got)
+        assert got[:upto] == [int(t) for t in want[:upto]]
+
+
 ROUTES = [pytest.param(3, id="simt"), pytest.param(0, id="tcgen05")]
 
 
@@ -53,7 +68,7 @@ def test_golden_nll_and_training_trajectory(torch_cuda, case, flags):
     losses = [eng.train_host(tokens[i]) for i in range(tokens.shape[0])]
     np.testing.assert_allclose(losses, g["losses"], rtol=1e-3)
     _, nll2 = eng.eval_host(tokens[0], return_nll=True)
-    assert rel_err(nll2, g["nll_after_training"]) < 2e-3  # 10 Adam steps of accumulated fp32/fp16 rounding
+    assert rel_err(nll2, g["nll_after_training"]) < NLL_RTOL  # still 1e-3 after 10 Adam steps
     eng.close()
 
 
@@ -134,14 +149,7 @@ def test_greedy_sampling_token_indices_bit_exact(torch_cuda, case, flags):
     n = len(g["sample"])
     got = eng.sample_host(3, n)
     assert (got[0] == got[1]).all() and (got[0] == got[2]).all()  # songs are independent and identical
-    want, margins = g["sample"].tolist(), g["sample_margins"]
-    for i in range(n):
-        if got[0, i] != want[i]:
-            assert margins[i] < TIE_MARGIN, f"token {i}: {got[0, i]} != {want[i]} with margin {margins[i]:.3e}"
-            break  # after a numerical tie the continuations legitimately differ
-    else:
-        return
-    assert i > 0
+    assert_greedy(O.glorot_init(cfg, 1234), got[0], g["sample"].tolist())
 
 
 @pytest.mark.parametrize("flags", SAMPLERS)
@@ -153,11 +161,7 @@ def test_sampling_long_sequence_matches_fp32_oracle(torch_cuda, flags):
     got = eng.sample_host(2, 96)[0].tolist()
     got_again = eng.sample_host(2, 96)[0].tolist()     # second call: cached split operands / P table
     assert got == got_again
-    want, margins = O.sample_greedy(params, 96, np.float64, True)
-    for i, (a, b) in enumerate(zip(got, want)):
-        if a != b:
-            assert margins[i] < TIE_MARGIN, (i, a, b, margins[i])
-            break
+    assert_greedy(params, got, O.sample_greedy(params, 96, np.float64))
 
 
 def _plugin_config(tmpdir=None, **over):
@@ -201,7 +205,8 @@ def test_plugin_class_train_eval_sample_like_the_reference(torch_cuda, tmp_path)
     big.set_params(params)
     ep2 = _Ep(*O.synthetic_episode(rng, 5, 5, 4, 12, 200))
     toks = np.concatenate([O.episode_train_tokens(e.support, e.query) for e in (ep, ep2)])
-    assert abs(big.train([ep, ep2]) - O.train_step(O.TrainState(params, cfg, np.float64), toks)) < 1e-2
+    want2 = O.train_step(O.TrainState(params, cfg, np.float64), toks)
+    assert abs(big.train([ep, ep2]) - want2) < 1e-3 * want2
 
 
 def test_checkpoint_save_recover_roundtrip(torch_cuda, tmp_path):
@@ -277,11 +282,8 @@ def test_sampling_after_training_uses_fresh_weights(torch_cuda):
         eng.train_host(tok)
     after = eng.sample_host(1, 24)[0].tolist()
     new_params = {k: v.astype(np.float32) for k, v in eng.export().items()}
-    want, margins = O.sample_greedy(new_params, 24, np.float64, True)
-    for i, (a, b) in enumerate(zip(after, want)):
-        if a != b:
-            assert margins[i] < TIE_MARGIN, (i, a, b, margins[i])
-            break
+    want = O.sample_greedy(new_params, 24, np.float64)
+    assert_greedy(new_params, after, want)
     assert before != after or before == want
 
 
