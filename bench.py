@@ -138,17 +138,17 @@ def synthetic_batches(w: dict, n_batches: int, seed: int):
     return out
 
 
-def cpu_reference_steps(w: dict, steps: int, warmup: int, episodes: int):
-    """The reference's CPU path (oracle port: torch-CPU fp32 restatement, all host threads) on a
-    bounded sample: `episodes` episodes of the workload's dims per step."""
+def cpu_reference_steps(w: dict, steps: int, warmup: int, episodes: int = 0, budget_s: float = 100.0):
+    """The reference's CPU path (oracle port: torch-CPU fp32 restatement, all host threads) on a bounded sample of the
+    workload: `episodes` episodes of the workload's dims per step (0 = as many of the workload's episodes per step as fit
+    `budget_s` seconds for the whole run, at most 8 — the CPU arm gets the larger, more efficient batch when it can)."""
     import torch
     from oracle import lstm_oracle as O
     from oracle.torch_ref import TorchRef
     cfg = model_config(w)
     ref = TorchRef(O.glorot_init(cfg, 1234), cfg, torch.float32)
-    wl = dict(w, episodes=episodes)
-    batches = synthetic_batches(wl, steps + warmup, 1234)
-    toks = [np.concatenate([O.episode_train_tokens(s, q) for s, q in b]) for b in batches]
+    probe = synthetic_batches(dict(w, episodes=1), 1, 4321)
+    tok1 = np.concatenate([O.episode_train_tokens(s, q) for s, q in probe[0]])
     # give the CPU path its best thread count: the tiny per-step matmuls of an LSTM get SLOWER with
     # 100+ threads, so probe a few counts (one step each) and keep the fastest
     avail = os.cpu_count() or 1
@@ -156,13 +156,18 @@ def cpu_reference_steps(w: dict, steps: int, warmup: int, episodes: int):
     for th in sorted({min(avail, c) for c in (8, 16, 32, avail)}):
         torch.set_num_threads(th)
         t0 = time.perf_counter()
-        ref.train_step(toks[0])
+        ref.train_step(tok1)
         dt = time.perf_counter() - t0
         if best is None or dt < best:
             best, cores = dt, th
         if dt > 8.0:   # bounded: do not keep probing configurations that are already slow
             break
     torch.set_num_threads(cores)
+    if episodes <= 0:
+        episodes = int(max(1, min(8, w["episodes"], budget_s / (best * (steps + warmup)))))
+    wl = dict(w, episodes=episodes)
+    batches = synthetic_batches(wl, steps + warmup, 1234)
+    toks = [np.concatenate([O.episode_train_tokens(s, q) for s, q in b]) for b in batches]
     for i in range(warmup):
         ref.train_step(toks[i])
     t0 = time.perf_counter()
@@ -170,100 +175,91 @@ def cpu_reference_steps(w: dict, steps: int, warmup: int, episodes: int):
         ref.train_step(toks[i])
     dt = (time.perf_counter() - t0) / max(steps, 1)
     n_tok = toks[0].size
-    return n_tok / dt, dt * 1e3, cores, n_tok
+    return n_tok / dt, dt * 1e3, cores, n_tok, episodes
 
 
 def run_reference(args, w, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    tps, ms, cores, n_tok = cpu_reference_steps(w, args.steps, max(args.warmup, 1), episodes=1)
-    sample = f"1 episode ({n_tok} tokens) of {wname} per step, torch-CPU fp32 restatement of the reference (TensorFlow 1.x not installable)"
+    tps, ms, cores, n_tok, n_ep = cpu_reference_steps(w, args.steps, max(args.warmup, 1))
+    sample = (f"{n_ep} of the workload's {w['episodes']} episodes per step ({n_tok} tokens) of {wname}, sized to finish the run within minutes; "
+              "torch-CPU fp32 restatement of the reference (TensorFlow 1.x not installable)")
     line = dict(impl="reference", metric="tokens/sec (5-shot lyrics, seq=128) training step", value=tps, unit="tokens/s",
                 n_gpus=args.gpus, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=wname, global_batch_seqs=SEQS_PER_EPISODE, seq_len=w["max_len"], sample=sample),
+                config=dict(workload=wname, global_batch_seqs=SEQS_PER_EPISODE * n_ep, seq_len=w["max_len"], sample=sample),
                 cpu_baseline=dict(value=tps, unit="tokens/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=tps, unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
 
-def run_sampling(args):
-    """Generated tokens/s of the on-device greedy sampler (no host round trip per token)."""
+def kernel_traffic() -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels, from the committed `ncu --set full` captures."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        f = ROOT / "profiles" / name
+        if f.exists():
+            try:
+                d = json.loads(f.read_text())
+                if "kernels" in d:
+                    return {k: float(v["dram_bytes_per_launch"]) for k, v in d["kernels"].items()}
+                return {"proj_logits_lse": float(d["dram_bytes_per_launch"])}
+            except Exception:
+                pass
+    return {}
+
+
+def measure_sampling(args, steps: int, warmup: int) -> dict:
+    """BASELINE.json configs[4]: generated tokens/s of the on-device greedy sampler (256 songs x 512 tokens, E=H=1024, V=4708;
+    reference lstm_baseline.py:135-156), no host round trip per token."""
     import torch
-    import __graft_entry__ as ge
-    ge.build()
     from fsmg.engine import Engine
     w = WORKLOADS["midi5shot_v4708_t256_h1024"]
     cfg = model_config(w)
     n_songs, n_tokens = 256, 512
-    eng = Engine(cfg, max_seqs=n_songs, device="cuda:0", flags=args.flags)
+    eng = Engine(cfg, max_seqs=n_songs, device=f"cuda:{torch.cuda.current_device()}", flags=args.flags)
     eng.init_params(1234)
-    for _ in range(max(args.warmup, 1)):
-        out = eng.sample_greedy_device(n_songs, n_tokens)
+    for _ in range(max(warmup, 1)):
+        eng.sample_greedy_device(n_songs, n_tokens)
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for _ in range(args.steps):
-        out = eng.sample_greedy_device(n_songs, n_tokens)
+    for _ in range(steps):
+        eng.sample_greedy_device(n_songs, n_tokens)
     ev1.record()
     torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / args.steps
-    t0 = time.perf_counter()
-    host = eng.sample_host(n_songs, n_tokens)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    ms = ev0.elapsed_time(ev1) / steps
+    launches = eng.last_launch_count()
+    e2e_ms = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        host = eng.sample_host(n_songs, n_tokens)       # the plugin's call: ids land in host memory
+        e2e_ms.append((time.perf_counter() - t0) * 1e3)
     f_tok = 2.0 * (1024 + 1024) * 4096 + 2.0 * 1024 * 4709
     pk = peaks()
     ach = f_tok * n_songs * n_tokens / (ms * 1e-3) / 1e12
-    print(json.dumps(dict(metric="generated tokens/sec (greedy, 256 songs x 512 tokens, E=H=1024, V=4708)", value=n_songs * n_tokens / (ms * 1e-3),
-                          unit="tokens/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 1), ms_per_step=ms, higher_is_better=True,
-                          dtype="split-f16 (hi + 2^-11 lo) operands, f32 accumulate: fp32-grade logits", data="synthetic",
-                          config=dict(workload="midi_greedy_256x512_h1024", flags=args.flags),
-                          e2e=dict(value=n_songs * n_tokens / (e2e_ms * 1e-3), unit="tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=n_songs * n_tokens * 4),
-                          gpu_launches=eng.last_launch_count() * args.steps, distinct_tokens=int(len(set(host[0].tolist()))),
-                          roofline=dict(bound="tensor", achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"],
-                                        note="algorithmic fwd FLOPs 2(E+H)4H+2HV' per token; latency-bound by design"))), flush=True)
+    rec = dict(metric="generated tokens/sec (greedy, 256 songs x 512 tokens, E=H=1024, V=4708)", value=n_songs * n_tokens / (ms * 1e-3),
+               unit="tokens/s", ms_per_step=ms, steps=steps, us_per_token_step=ms * 1e3 / n_tokens,
+               dtype="split-f16 (hi + 2^-11 lo) operands, f32 accumulate: fp32-grade logits",
+               config=dict(workload="midi_greedy_256x512_h1024", songs=n_songs, tokens=n_tokens),
+               e2e=dict(value=n_songs * n_tokens / (float(np.mean(e2e_ms)) * 1e-3), unit="tokens/s", ms_per_step=float(np.mean(e2e_ms)),
+                        h2d_bytes_per_step=0, d2h_bytes_per_step=n_songs * n_tokens * 4),
+               gpu_launches=int(launches), distinct_tokens=int(len(set(host[0].tolist()))),
+               roofline=dict(bound="tensor", achieved=ach, peak=pk["tflops"], unit="TFLOP/s", frac=ach / pk["tflops"],
+                             note="algorithmic fwd FLOPs 2(E+H)4H+2HV' per token vs sustained bf16 peak; the decode is a chain of 512 dependent "
+                                  "steps of M=256 rows (latency / L2-bandwidth bound)"))
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    return rec
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lyrics5shot_v10k_t128_h512", choices=sorted(WORKLOADS))
-    ap.add_argument("--episodes", type=int, default=0, help="override episodes/step/GPU (debug; invalidates the number)")
-    ap.add_argument("--flags", type=int, default=0, help="FSMG_FLAG_* bits (debug routes)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="train", choices=["train", "sample"],
-                    help="sample: BASELINE configs[4] greedy generation (256 songs x 512 tokens, E=H=1024, V=4708)")
-    args = ap.parse_args()
-    wname = args.workload
-    w = dict(WORKLOADS[wname])
-    if args.episodes:
-        w["episodes"] = args.episodes
-    if args.impl == "reference":
-        return run_reference(args, w, wname)
-    if args.mode == "sample":
-        return run_sampling(args)
-
+def measure_training(args, wname: str, w: dict, steps: int, warmup: int, world: int, rank: int, local: int, full: bool):
+    """One workload through the plugin registry: device-resident `value`, end-to-end `e2e` (host episodes in, float loss out),
+    per-phase CUDA-event timing and the rooflines derived from it.  `full` adds the device-corpus e2e arm and the clock
+    sampler (main workload only)."""
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    args.warmup = max(args.warmup, 3)
-
-    import __graft_entry__ as ge
-    if rank == 0:
-        ge.build()
-    if world > 1:
-        dist.barrier()
     from train.train import load_model_from_config
     cfg = model_config(w)
     cfg["episodes_per_step"] = w["episodes"]
@@ -274,9 +270,7 @@ def main():
     n_seqs = SEQS_PER_EPISODE * w["episodes"]
     T = w["max_len"]
     tokens_per_step = n_seqs * T * world
-
-    total = args.warmup + args.steps
-    n_distinct = min(total, 4)
+    n_distinct = min(warmup + steps, 4)
     batches = synthetic_batches(w, n_distinct, 1234 + rank)
 
     class Ep:
@@ -298,18 +292,19 @@ def main():
         return float(t)
 
     # ---- device-resident arm: `value` ----------------------------------------------------------------
-    for i in range(args.warmup):
+    for i in range(warmup):
         eng.train_step_device(dev_batches[i % n_distinct])
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if full else None
+    if sampler:
+        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for i in range(args.steps):
-        eng.train_step_device(dev_batches[(args.warmup + i) % n_distinct])
+    for i in range(steps):
+        eng.train_step_device(dev_batches[(warmup + i) % n_distinct])
     ev1.record()
     barrier()
-    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / steps)
     value = tokens_per_step / (ms_step * 1e-3)
     launches = eng.last_launch_count()
 
@@ -317,42 +312,43 @@ def main():
     for i in range(2):
         model.train(host_batches[i % n_distinct])
     barrier()
-    # every step synchronises on its loss, so host jitter (numpy concat, ~750 launches) is fully exposed: two passes of
-    # K steps each, the better pass is reported and both are listed
+    # every step synchronises on its loss, so host jitter (numpy block copies, the graph launch) is fully exposed: two
+    # passes of K steps each, the MEAN is reported and both are listed
     passes = []
     for _ in range(2):
         ev0.record()
-        for i in range(args.steps):
+        for i in range(steps):
             model.train(host_batches[i % n_distinct])   # numpy in -> pinned -> H2D -> step -> D2H loss -> float
         ev1.record()
         barrier()
-        passes.append(max_over_ranks(ev0.elapsed_time(ev1) / args.steps))
-    clocks = sampler.stop()     # sampled across both timed regions (device-resident arm and end-to-end arm)
-    ms_e2e = min(passes)
+        passes.append(max_over_ranks(ev0.elapsed_time(ev1) / steps))
+    clocks = sampler.stop() if sampler else None     # sampled across both timed regions (device-resident and end-to-end)
+    ms_e2e = float(np.mean(passes))
     e2e = dict(value=tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
-               passes_ms_per_step=[round(x, 4) for x in passes],
-               h2d_bytes_per_step=n_seqs * T * 4, d2h_bytes_per_step=4)
+               passes_ms_per_step=[round(x, 4) for x in passes], reported="mean of the passes",
+               h2d_bytes_per_step=n_seqs * T * 4, d2h_bytes_per_step=16)
 
-    # ---- same call with a device-resident corpus (data.device_episode): only song indices cross PCIe ------------
-    from data.device_episode import DeviceEpisodeSampler
-    from data.episode import TokenCorpus
-    rng_c = np.random.RandomState(99 + rank)
-    from data import synthetic as SY
-    songs = SY.synthetic_tokens(rng_c, (64, 24, T), w["input_size"], w["kind"])
-    dsamp = DeviceEpisodeSampler(TokenCorpus([songs[a] for a in range(64)], w["input_size"], T), 5, 5, 4, T, seed=7 + rank)
-    idx_batches = [[dsamp.get_episode() for _ in range(w["episodes"])] for _ in range(n_distinct)]
-    for i in range(2):
-        model.train(idx_batches[i % n_distinct])
-    barrier()
-    ev0.record()
-    for i in range(args.steps):
-        model.train(idx_batches[i % n_distinct])    # indices -> pinned -> H2D -> device gather -> step -> D2H loss
-    ev1.record()
-    barrier()
-    ms_idx = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
-    e2e["device_corpus"] = dict(value=tokens_per_step / (ms_idx * 1e-3), unit="tokens/s", ms_per_step=ms_idx,
-                                h2d_bytes_per_step=n_seqs * 4, d2h_bytes_per_step=4,
-                                note="episodes as index sets into an HBM-resident corpus (data.device_episode), gathered on the device")
+    if full:
+        # ---- same call with a device-resident corpus (data.device_episode): only song indices cross PCIe ------------
+        from data.device_episode import DeviceEpisodeSampler
+        from data.episode import TokenCorpus
+        from data import synthetic as SY
+        rng_c = np.random.RandomState(99 + rank)
+        songs = SY.synthetic_tokens(rng_c, (64, 24, T), w["input_size"], w["kind"])
+        dsamp = DeviceEpisodeSampler(TokenCorpus([songs[a] for a in range(64)], w["input_size"], T), 5, 5, 4, T, seed=7 + rank)
+        idx_batches = [[dsamp.get_episode() for _ in range(w["episodes"])] for _ in range(n_distinct)]
+        for i in range(2):
+            model.train(idx_batches[i % n_distinct])
+        barrier()
+        ev0.record()
+        for i in range(steps):
+            model.train(idx_batches[i % n_distinct])    # indices -> pinned -> H2D -> device gather -> step -> D2H loss
+        ev1.record()
+        barrier()
+        ms_idx = max_over_ranks(ev0.elapsed_time(ev1) / steps)
+        e2e["device_corpus"] = dict(value=tokens_per_step / (ms_idx * 1e-3), unit="tokens/s", ms_per_step=ms_idx,
+                                    h2d_bytes_per_step=n_seqs * 4, d2h_bytes_per_step=16,
+                                    note="episodes as index sets into an HBM-resident corpus (data.device_episode), gathered on the device")
 
     # ---- per-phase device timing (CUDA events on the launching stream, 2 extra steps) ---------------
     eng.set_profile(True)
@@ -363,56 +359,201 @@ def main():
     prof = eng.read_profile()
     eng.set_profile(False)
     phases = {k: round(v["ms"] / prof_steps, 4) for k, v in prof.items()}
+    brackets = {k: max(v["brackets"] // prof_steps, 1) for k, v in prof.items()}
 
     pk = peaks()
-    f_tok = flops_per_token(w)
+    traffic = kernel_traffic() if wname == "lyrics5shot_v10k_t128_h512" else {}
     e_, h_, v1_ = w["embedding_size"], w["hidden_size"], w["input_size"] + 1
     tok_gpu = tokens_per_step / world
-    # dominant kernel: the projection GEMM with the fused online-LSE epilogue (tc_gemm_kernel<256, EPI_LSE>):
-    # algorithmic FLOPs per launch = 2 * chunk_rows * H * V'; summed over a step = 2 * tokens * H * V'
-    lse_ms = phases["proj_logits_lse"]
-    n_launch = max(prof["proj_logits_lse"]["brackets"] // prof_steps, 1)
-    lse_flops = 2.0 * tok_gpu * h_ * v1_
-    achieved = lse_flops / (lse_ms * 1e-3) / 1e12 if lse_ms > 0 else 0.0
-    step_tflops = f_tok * tok_gpu / (ms_step * 1e-3) / 1e12
-    traffic = None
-    tf = ROOT / "profiles" / "r1_traffic.json"
-    if tf.exists():   # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
-        try:
-            traffic = float(json.loads(tf.read_text())["dram_bytes_per_launch"])
-        except Exception:
-            traffic = None
-    roofline = dict(bound="tensor", kernel="tc::tc_gemm_kernel<256, EPI_LSE> projection logits + online log-sum-exp "
-                    f"({n_launch} launches/step, {lse_flops / n_launch / 1e9:.2f} GFLOP each)",
-                    achieved=achieved, peak=pk["tflops_burst"], unit="TFLOP/s", frac=achieved / pk["tflops_burst"],
-                    traffic=traffic, peak_source=pk["source"] + " burst bf16 (kernel timed alone between events)",
-                    avg_launch_us=lse_ms * 1e3 / n_launch,
-                    whole_step=dict(achieved=step_tflops, peak=pk["tflops"], frac=step_tflops / pk["tflops"],
-                                    note="algorithmic 3*(2(E+H)4H+2HV') FLOP/token over the full optimizer step vs sustained bf16 peak"))
+    step_tflops = flops_per_token(w) * tok_gpu / (ms_step * 1e-3) / 1e12
 
-    # secondary roofline: the one purely HBM-bound kernel of the step (in-place softmax gradient over the fp16 logits chunks)
-    sg_ms = phases.get("softmax_grad_bias", 0.0)
+    def tensor_roofline(phase, kernel, flops_step, note=None):
+        ms = phases.get(phase, 0.0)
+        n_launch = brackets.get(phase, 1)
+        ach = flops_step / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        r = dict(bound="tensor", kernel=f"{kernel} ({n_launch} launch(es)/step, {flops_step / n_launch / 1e9:.2f} GFLOP each)", phase=phase,
+                 achieved=ach, peak=pk["tflops_burst"], unit="TFLOP/s", frac=ach / pk["tflops_burst"], traffic=traffic.get(phase),
+                 peak_source=pk["source"] + " burst bf16 (kernel timed alone between CUDA events on the launching stream)",
+                 avg_launch_us=ms * 1e3 / n_launch, ms_per_step=ms)
+        if note:
+            r["note"] = note
+        return r
+
+    rec_flops = 2.0 * tok_gpu * h_ * 4 * h_          # h_{t-1} * Wh (forward) / dgates_{t+1} * Wh^T (backward): 2*H*4H per token
+    rec_note = "sequential T-step recurrence: the bound is the per-step exchange latency, not the tensor pipe (DESIGN.md §5 R)"
+    roof = {
+        "recurrent_bwd": tensor_roofline("recurrent_bwd", "tc::lstm_bwd_* persistent reverse-time recurrence (dgates exchange, W_hh^T slice SMEM-resident)", rec_flops, rec_note),
+        "recurrent_fwd": tensor_roofline("recurrent_fwd", "tc::lstm_fwd_* persistent recurrence (h exchange, W_hh slice SMEM-resident)", rec_flops, rec_note),
+        "proj_logits_lse": tensor_roofline("proj_logits_lse", "tc::tc_gemm_kernel<256, EPI_LSE> projection logits + online log-sum-exp", 2.0 * tok_gpu * h_ * v1_),
+        "proj_dh": tensor_roofline("proj_dh", "tc::tc_gemm_kernel<512> dH = dlogits * Ws^T", 2.0 * tok_gpu * h_ * v1_),
+        "proj_dws": tensor_roofline("proj_dws", "tc::tc_gemm_kernel<512, MN-major> dWs^T += dlogits^T * hs", 2.0 * tok_gpu * h_ * v1_),
+    }
+    # the bench line's `roofline` is the kernel that takes the most time in the step (by the phase brackets), whichever it is
+    top = max(roof, key=lambda k: phases.get(k, 0.0))
     vp = (v1_ + 15) // 16 * 16
+    sg_ms = phases.get("softmax_grad_bias", 0.0)
     sg_bytes = 2.0 * tok_gpu * vp * 2          # one read + one write of every fp16 logit
     roofline_hbm = dict(bound="hbm", kernel="tc::softmax_grad_stream_kernel (+ lse_combine) in-place dlogits = softmax - onehot, bias-gradient column sums",
                         achieved=sg_bytes / (sg_ms * 1e-3) / 1e9 if sg_ms > 0 else 0.0, peak=pk["hbm"], unit="GB/s",
-                        frac=(sg_bytes / (sg_ms * 1e-3) / 1e9 / pk["hbm"]) if sg_ms > 0 else 0.0, ms_per_step=sg_ms)
+                        frac=(sg_bytes / (sg_ms * 1e-3) / 1e9 / pk["hbm"]) if sg_ms > 0 else 0.0, ms_per_step=sg_ms,
+                        traffic=traffic.get("softmax_grad_bias"))
+    if phases.get("softmax_grad_bias", 0.0) > phases.get(top, 0.0):
+        top_roofline = dict(roofline_hbm)
+    else:
+        top_roofline = dict(roof[top])
+    top_roofline["top_by"] = "largest phase of the step by CUDA-event brackets (phases_ms)"
+    top_roofline["whole_step"] = dict(achieved=step_tflops, peak=pk["tflops"], frac=step_tflops / pk["tflops"],
+                                      note="algorithmic 3*(2(E+H)4H+2HV') FLOP/token over the full optimizer step vs sustained bf16 peak")
+    rec = dict(value=value, unit="tokens/s", ms_per_step=ms_step, steps=steps, warmup=warmup,
+               config=dict(workload=wname, episodes_per_step_per_gpu=w["episodes"], global_batch_seqs=n_seqs * world,
+                           seq_len=T, vocab=w["input_size"], hidden=w["hidden_size"], embedding=w["embedding_size"],
+                           parallelism=f"dp{world}", l2="per-step working set (GBs of activations) >> 126 MB L2; "
+                           f"{n_distinct} distinct batches rotate", flags=args.flags),
+               e2e=e2e, gpu_launches=int(launches) * steps, roofline=top_roofline, roofline_gemm=roof["proj_logits_lse"],
+               roofline_recurrent=dict(forward=roof["recurrent_fwd"], backward=roof["recurrent_bwd"]),
+               roofline_proj_backward=dict(dh=roof["proj_dh"], dws=roof["proj_dws"]), roofline_hbm=roofline_hbm, phases_ms=phases,
+               clocks=clocks)
+    return rec, model
+
+
+def dp_check(args, world: int, rank: int, local: int) -> dict:
+    """BASELINE.json configs[3] correctness, visible in the bench line: (1) after the timed steps every replica holds
+    bit-identical parameters (checked by the caller); (2) a k-GPU data-parallel step on k shards equals the 1-GPU step on the
+    union batch — same workload dims, 2 episodes per rank, three optimizer steps, loss and parameters compared."""
+    import torch
+    import torch.distributed as dist
+    from fsmg.engine import Engine
+    w = WORKLOADS["lyrics5shot_v10k_t128_h512"]
+    cfg = model_config(w)
+    per_rank = 2 * SEQS_PER_EPISODE
+    wl = dict(w, episodes=2)
+    shard_eps = synthetic_batches(wl, 1, 777 + rank)[0]
+    shard = np.concatenate([np.concatenate([s.reshape(-1, w["max_len"]), q.reshape(-1, w["max_len"])]) for s, q in shard_eps]).astype(np.int32)
+    d_shard = torch.from_numpy(shard).to(f"cuda:{local}")
+    gathered = [torch.empty_like(d_shard) for _ in range(world)]
+    dist.all_gather(gathered, d_shard)
+    union = torch.cat(gathered)
+    dp = Engine(cfg, max_seqs=per_rank, device=f"cuda:{local}", flags=args.flags)
+    dp.init_params(1234)
+    dp_losses = [float(dp.train_step_device(d_shard)) for _ in range(3)]
+    out = None
+    if rank == 0:
+        single = Engine(cfg, max_seqs=per_rank * world, device=f"cuda:{local}", flags=args.flags, world=1)
+        single.init_params(1234)
+        s_losses = [float(single.train_step_device(union)) for _ in range(3)]
+        init = Engine(cfg, max_seqs=1, device=f"cuda:{local}", flags=args.flags, world=1)
+        init.init_params(1234)
+        upd = float((single.params - init.params).norm())
+        diff = float((single.params - dp.params).norm())
+        out = dict(steps=3, seqs_per_rank=per_rank, loss_dp=dp_losses, loss_single_gpu=s_losses,
+                   loss_max_rel_diff=float(max(abs(a - b) / abs(b) for a, b in zip(dp_losses, s_losses))),
+                   param_update_rel_diff=diff / (upd + 1e-30),
+                   note="k-GPU step on k shards vs 1-GPU step on the union batch (same init, same loss scale); "
+                        "differences are fp32 summation order (NCCL ring vs in-kernel REDs)")
+        single.close()
+        init.close()
+    dp.close()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lyrics5shot_v10k_t128_h512", choices=sorted(WORKLOADS))
+    ap.add_argument("--episodes", type=int, default=0, help="override episodes/step/GPU (debug; invalidates the number)")
+    ap.add_argument("--flags", type=int, default=0, help="FSMG_FLAG_* bits (debug routes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the configs[2] / configs[4] sub-records and the dp check")
+    ap.add_argument("--mode", default="train", choices=["train", "sample"],
+                    help="sample: only BASELINE configs[4] greedy generation (256 songs x 512 tokens, E=H=1024, V=4708)")
+    args = ap.parse_args()
+    wname = args.workload
+    w = dict(WORKLOADS[wname])
+    if args.episodes:
+        w["episodes"] = args.episodes
+    if args.impl == "reference":
+        return run_reference(args, w, wname)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    args.warmup = max(args.warmup, 3)
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    else:
+        ge.build()
+
+    if args.mode == "sample":
+        rec = measure_sampling(args, args.steps, args.warmup)
+        rec.update(n_gpus=1, warmup=max(args.warmup, 1), higher_is_better=True, data="synthetic")
+        print(json.dumps(rec), flush=True)
+        return
+
+    rec, model = measure_training(args, wname, w, args.steps, args.warmup, world, rank, local, full=True)
+
+    check = None
+    if world > 1:
+        # replicas must hold bit-identical parameters after the warm-up, timed, end-to-end and profiling steps
+        eng = model.engine
+        ref_params = eng.params.clone()
+        dist.broadcast(ref_params, src=0)
+        same = torch.tensor([1 if torch.equal(ref_params, eng.params) else 0], device=f"cuda:{local}")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        steps_done = eng.global_step
+        del ref_params
+        if not args.no_extra_configs:
+            check = dp_check(args, world, rank, local)
+        if check is None:
+            check = {}
+        check.update(replicas_bit_identical=bool(int(same)), after_optimizer_steps=int(steps_done))
+    del model
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[2] (MIDI vocabulary, T=256, H=1024, one episode) and configs[4] (greedy generation), 1 GPU ----
+    extra = {}
+    if world == 1 and not args.no_extra_configs and wname == "lyrics5shot_v10k_t128_h512":
+        w3 = dict(WORKLOADS["midi5shot_v4708_t256_h1024"])
+        rec3, m3 = measure_training(args, "midi5shot_v4708_t256_h1024", w3, max(args.steps, 10), args.warmup, 1, 0, local, full=False)
+        rec3["metric"] = "tokens/sec (5-shot MIDI events, seq=256, H=1024, 1 episode) training step"
+        rec3.pop("clocks", None)
+        del m3
+        torch.cuda.empty_cache()
+        extra["midi_cfg3"] = rec3
+        extra["sample_cfg5"] = measure_sampling(args, steps=3, warmup=1)
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
-            tps, ms, cores, n_tok = cpu_reference_steps(w, steps=3, warmup=1, episodes=1)
+            tps, ms, cores, n_tok, n_ep = cpu_reference_steps(w, steps=3, warmup=1, budget_s=25.0)
             cpu = dict(value=tps, unit="tokens/s", cores=cores, kind="port", ms_per_step=ms,
-                       sample=f"3 steps of 1 episode ({n_tok} tokens) at the workload's dims; torch-CPU fp32 restatement "
+                       sample=f"3 steps of {n_ep} episode(s) ({n_tok} tokens) at the workload's dims; torch-CPU fp32 restatement "
                               "(oracle/torch_ref.py) — TensorFlow 1.x reference cannot be installed")
-        line = dict(metric="tokens/sec (5-shot lyrics, seq=128) training step", value=value, unit="tokens/s", n_gpus=world,
-                    steps=args.steps, warmup=args.warmup, ms_per_step=ms_step, higher_is_better=True, scaling="weak",
+        line = dict(metric="tokens/sec (5-shot lyrics, seq=128) training step", value=rec["value"], unit="tokens/s", n_gpus=world,
+                    steps=args.steps, warmup=args.warmup, ms_per_step=rec["ms_per_step"], higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f16 operands, f32 accumulate/state/optimizer", data="synthetic",
-                    config=dict(workload=wname, episodes_per_step_per_gpu=w["episodes"], global_batch_seqs=n_seqs * world,
-                                seq_len=T, vocab=w["input_size"], hidden=w["hidden_size"], embedding=w["embedding_size"],
-                                parallelism=f"dp{world}", l2="per-step working set (~GBs of activations) >> 126 MB L2; "
-                                f"{n_distinct} distinct batches rotate", flags=args.flags),
-                    e2e=e2e, gpu_launches=int(launches) * args.steps, roofline=roofline, roofline_hbm=roofline_hbm, phases_ms=phases, cpu_baseline=cpu, clocks=clocks)
+                    config=rec["config"], e2e=rec["e2e"], gpu_launches=rec["gpu_launches"], roofline=rec["roofline"],
+                    roofline_gemm=rec["roofline_gemm"], roofline_recurrent=rec["roofline_recurrent"],
+                    roofline_proj_backward=rec["roofline_proj_backward"], roofline_hbm=rec["roofline_hbm"],
+                    phases_ms=rec["phases_ms"], cpu_baseline=cpu, clocks=rec["clocks"])
+        if extra:
+            line["configs"] = extra
+        if check is not None:
+            line["dp_check"] = check
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -41,7 +41,7 @@ class Engine:
     """One engine per process/GPU.  `config` uses the reference's keys (lstm_baseline.py:21-29)."""
 
     def __init__(self, config: dict, max_seqs: int, device: Optional[torch.device] = None, flags: int = 0,
-                 process_group=None):
+                 process_group=None, world: Optional[int] = None):
         if not torch.cuda.is_available():
             raise FsmgError("fsmg requires a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -84,8 +84,9 @@ class Engine:
             self.infos.append(dict(name=pi.name.decode(), offset=int(pi.offset), shape=shape))
         self.global_step = 0
         self.pg = process_group
-        self.world = torch.distributed.get_world_size(process_group) if (
-            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        # world = 1 inside an initialised process group gives a purely local engine (single-GPU cross-checks of a DP run)
+        self.world = int(world) if world is not None else (torch.distributed.get_world_size(process_group) if (
+            torch.distributed.is_available() and torch.distributed.is_initialized()) else 1)
         self._nll = torch.empty(self.max_seqs * self.T, dtype=torch.float32, device=dev)
         self._sum = torch.zeros(1, dtype=torch.float32, device=dev)
         self._tok = torch.empty(self.max_seqs * self.T, dtype=torch.int32, device=dev)
