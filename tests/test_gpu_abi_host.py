@@ -116,8 +116,9 @@ def test_host_abi_train_eval_sample_follow_the_oracle(torch_cuda, built_lib):
         assert abs(out.value - want) < 1e-3 * want
     got = raw.read_params()
     for k, v in state.params.items():
-        scale = np.abs(v - params[k]).max() + 1e-12             # compare the 4-step UPDATE, not the value
-        assert np.abs(got[k].reshape(v.shape) - v).max() < 0.05 * scale, k
+        # compare the 4-step UPDATE, norm-wise (Adam turns a near-zero gradient whose sign differs by rounding into a full-size step)
+        upd = np.linalg.norm(v - params[k]) + 1e-12
+        assert np.linalg.norm(got[k].reshape(v.shape) - v) < 0.05 * upd, k
     # LSTMBaseline.sample(support_set, num): greedy, support ignored, ids on the host
     num = 20
     ids = np.empty((2, num), np.int32)
