@@ -125,6 +125,10 @@ struct fsmg_handle {
     struct StepGraph { int32_t n; uint32_t ls_bits; float* nll; cudaGraphExec_t exec; int64_t launches; int seen; int failed; };
     std::vector<StepGraph> step_graphs;
     int use_graph = 1;
+    // caller-owned events recorded INSIDE forward_backward (fsmg_set_stage_events): [0] softmax_w / softmax_b gradients final (after the
+    // projection backward), [1] embedding gradient final.  A data-parallel caller all-reduces those slices on a side stream while the
+    // recurrent backward still runs.
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
     fsmg::TcContext tc;
 };
 
@@ -142,6 +146,16 @@ struct ProfScope {
         if (a) { cudaEvent_t b = h->prof.get(); cudaEventRecord(b, s); h->prof.recs.push_back({ph, a, b}); }
     }
 };
+
+// records a caller-owned stage event on s; inside a stream capture it becomes an external event-record node of the graph
+static int record_stage_event(fsmg_handle* h, int which, cudaStream_t s) {
+    cudaEvent_t ev = h->stage_ev[which];
+    if (!ev) return FSMG_OK;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    FSMG_CUDA_OK(cudaStreamIsCapturing(s, &st));
+    FSMG_CUDA_OK(cudaEventRecordWithFlags(ev, s, st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault));
+    return FSMG_OK;
+}
 
 // bump allocator used twice: sizing (base == nullptr) and carving
 struct Bump {
@@ -593,6 +607,12 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
             h->launches += 5;
             FSMG_LAUNCH_OK();
             float* gK0 = h->grads + l.k_off;
+            // dEmbedding = loss_scale * S * K[:E]^T   (dense [V', E]; rows of words absent from the batch come out zero).  First of the three
+            // GEMMs: the embedding gradient is the largest slice of the flat buffer, and a data-parallel caller starts its all-reduce from the
+            // stage event while the two kernel-gradient GEMMs and the occurrence-norm pass below still run
+            rc = gemm_f16(h, mk(V1, h->E, h->G4, h->seg16, h->G4p, l.K16, h->G4p, h->grads + h->emb_off, h->E, loss_scale), false, false, s);
+            if (rc) return rc;
+            if ((rc = record_stage_event(h, 1, s))) return rc;
             // dK[:E] = loss_scale * embedding^T * S   (contraction over the V' words)
             rc = gemm_f16(h, mk(l.in, h->G4, V1, h->emb16, h->Ep, h->seg16, h->G4p, gK0, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
             if (rc) return rc;
@@ -602,9 +622,6 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
                                     gK0 + (int64_t)l.in * h->G4, h->G4, loss_scale, nullptr, 0, 0, 1), true, true, s);
                 if (rc) return rc;
             }
-            // dEmbedding = loss_scale * S * K[:E]^T   (dense [V', E]; rows of words absent from the batch come out zero)
-            rc = gemm_f16(h, mk(V1, h->E, h->G4, h->seg16, h->G4p, l.K16, h->G4p, h->grads + h->emb_off, h->E, loss_scale), false, false, s);
-            if (rc) return rc;
         }
         if (seg) {
             // per-occurrence square norm of the IndexedSlices rows: ||loss_scale * dgates[r,:] * K[:E]^T||^2 summed over tokens (A.6)
@@ -656,6 +673,7 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
                 LAUNCH_COUNT(h);
             }
         }
+        if (li == 0 && (rc = record_stage_event(h, 1, s))) return rc;   // embedding gradient final (scatter / epilogue route)
         cur ^= 1;
     }
     FSMG_LAUNCH_OK();
@@ -940,6 +958,7 @@ static int enqueue_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int
     if (rc) return rc;
     rc = projection(h, n_seqs, true, loss_scale, d_nll, s);
     if (rc) return rc;
+    if ((rc = record_stage_event(h, 0, s))) return rc;   // softmax_w / softmax_b gradients are final
     sum_f32_kernel<<<148, 256, 0, s>>>(d_nll ? d_nll : h->nll, (int64_t)n_seqs * h->T, h->grads + h->n_params);
     LAUNCH_COUNT(h);
     rc = backward_lstm(h, n_seqs, loss_scale, s);
@@ -992,6 +1011,29 @@ int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seq
     }
     FSMG_CUDA_OK(cudaGraphLaunch(g->exec, s));
     h->launches = g->launches;
+    return FSMG_OK;
+}
+
+int fsmg_set_stage_events(fsmg_handle* h, void* ev_softmax_grads, void* ev_embedding_grads, int32_t reserve_sms) {
+    if (!h) return set_error(FSMG_ERR_INVALID, "null handle");
+    if (reserve_sms < 0 || reserve_sms > 64) return set_error(FSMG_ERR_INVALID, "reserve_sms outside [0, 64]");
+    h->stage_ev[0] = (cudaEvent_t)ev_softmax_grads;
+    h->stage_ev[1] = (cudaEvent_t)ev_embedding_grads;
+    h->tc.lstm_reserve_sms = reserve_sms;
+    for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // captured graphs hold the old events / grid sizes
+    h->step_graphs.clear();
+    return FSMG_OK;
+}
+
+int fsmg_param_range(const fsmg_handle* h, int32_t which, int64_t* begin, int64_t* end) {
+    if (!h || !begin || !end) return set_error(FSMG_ERR_INVALID, "null argument");
+    switch (which) {
+        case 0: *begin = h->emb_off; *end = h->dense_begin; break;          // embedding
+        case 1: *begin = h->dense_begin; *end = h->sw_off; break;           // LSTM kernels and biases
+        case 2: *begin = h->sw_off; *end = h->n_params; break;              // softmax_w, softmax_b
+        case 3: *begin = h->n_params; *end = h->n_params + FSMG_GRAD_EXTRA; break;   // piggy-backed scalars (gradient buffer only)
+        default: return set_error(FSMG_ERR_INVALID, "range index outside [0, 3]");
+    }
     return FSMG_OK;
 }
 

@@ -1068,6 +1068,7 @@ struct TcContext {
     int lstm_pair = 0;         // persistent backward kernel as cta_group::2 pairs (each CTA ingests half of the exchanged rows)
     int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
+    int lstm_reserve_sms = 0;  // SMs the persistent recurrent kernels leave free (for the NCCL kernels of an overlapped gradient all-reduce)
 };
 
 template <typename B>

@@ -998,7 +998,10 @@ static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, bool want_pai
     while (cls > 1 && (pl.C % cls) != 0) cls >>= 1;
     pl.cls = cls;
     // clusters of 4 cannot use every SM (GPC sizes are not multiples of 4): 132 co-resident CTAs at most
-    const int sms = cls == 4 ? (c.num_sms < 132 ? c.num_sms / 4 * 4 : 132) : c.num_sms;
+    // lstm_reserve_sms: every CTA of these cooperative kernels must be resident at once; the SMs left free host the (few-CTA) NCCL
+    // kernels of a gradient all-reduce that overlaps the backward pass (fsmg_set_stage_events)
+    const int usable = c.num_sms - c.lstm_reserve_sms > 0 ? c.num_sms - c.lstm_reserve_sms : c.num_sms;
+    const int sms = cls == 4 ? (usable < 132 ? usable / 4 * 4 : 132) : usable;
     int gmax = sms / pl.C;
     if (gmax < 1) return pl;
     int mg = cdiv(N, gmax);

@@ -96,6 +96,59 @@ class Engine:
         self._ids: Optional[torch.Tensor] = None
         self._pinned_np = None
         self._checked_corpora = set()
+        self._overlap = False
+        if self.world > 1 and os.environ.get("FSMG_AR_OVERLAP", "1") != "0":
+            self._setup_overlapped_allreduce()
+
+    # ---- data-parallel gradient all-reduce overlapped with the backward pass ----------------------------------------
+    AR_CTAS = 4      # CTAs of the side communicator's kernels = SMs the persistent recurrent kernels leave free
+
+    def _setup_overlapped_allreduce(self) -> None:
+        """The flat gradient buffer is reduced in slices as they become final (stage events recorded inside the library's
+        CUDA graph): softmax_w|softmax_b after the projection backward and the embedding after its GEMM — both on a side
+        stream through a communicator limited to AR_CTAS CTAs, while the recurrent backward (which leaves AR_CTAS SMs free)
+        and the kernel-gradient GEMMs run — then only the LSTM kernels/biases and the 8 scalars after the call."""
+        import torch.distributed as dist
+        try:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = self.AR_CTAS
+            opts.config.min_ctas = 1
+            self._pg_side = dist.new_group(backend="nccl", pg_options=opts)
+        except Exception:           # no NCCL config support: keep the single all-reduce
+            return
+        self._ranges = []
+        for which in range(4):
+            b, e = C.c_int64(), C.c_int64()
+            _lib.check(self.lib.fsmg_param_range(self.h, which, C.byref(b), C.byref(e)))
+            self._ranges.append((int(b.value), int(e.value)))
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ev_soft, self._ev_emb = torch.cuda.Event(), torch.cuda.Event()
+        for ev in (self._ev_soft, self._ev_emb):
+            ev.record(torch.cuda.current_stream(self.device))     # materialises the cudaEvent_t
+        _lib.check(self.lib.fsmg_set_stage_events(self.h, self._ev_soft.cuda_event, self._ev_emb.cuda_event, self.AR_CTAS))
+        # warm both communicators up (lazy NCCL init would otherwise land inside the first step)
+        probe = torch.zeros(8, device=self.device)
+        dist.all_reduce(probe, group=self._pg_side)
+        dist.all_reduce(probe, group=self.pg)
+        torch.cuda.synchronize(self.device)
+        self._overlap = True
+
+    def _all_reduce_grads(self) -> None:
+        import torch.distributed as dist
+        if not self._overlap:
+            dist.all_reduce(self.grads, group=self.pg)
+            return
+        main = torch.cuda.current_stream(self.device)
+        g, (emb, rnn, soft, extra) = self.grads, self._ranges
+        self._side.wait_event(self._ev_soft)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(g[soft[0]:soft[1]], group=self._pg_side)
+        self._side.wait_event(self._ev_emb)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(g[emb[0]:emb[1]], group=self._pg_side)
+        dist.all_reduce(g[rnn[0]:rnn[1]], group=self.pg)          # after the whole backward pass, on the caller's stream
+        dist.all_reduce(g[extra[0]:extra[1]], group=self.pg)
+        main.wait_stream(self._side)
 
     # ---- parameters ---------------------------------------------------------------------------
     def param_shapes(self) -> Dict[str, tuple]:
@@ -166,7 +219,7 @@ class Engine:
         gt = global_tokens if global_tokens is not None else n * self.T * self.world
         self.forward_backward(tokens, gt)
         if self.world > 1:
-            torch.distributed.all_reduce(self.grads, group=self.pg)
+            self._all_reduce_grads()
         _lib.check(self.lib.fsmg_apply_update(self.h, self.global_step, 0, self._stream()))
         self.global_step += 1
         self._last_gt = float(gt)

@@ -122,6 +122,18 @@ int fsmg_forward_nll(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs,
 int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seqs,
                           float loss_scale, float* d_nll, void* stream);
 
+/* Overlapping the data-parallel all-reduce with the backward pass.  The caller hands in two of its own cudaEvent_t
+ * (void*, may be NULL): fsmg_forward_backward records ev_softmax_grads on `stream` as soon as the softmax_w / softmax_b
+ * gradients are final (after the projection backward, before the recurrent backward) and ev_embedding_grads as soon as
+ * the embedding gradient is final; inside the library's CUDA graph they are external event-record nodes.  The caller
+ * makes a side stream wait on them and all-reduces fsmg_param_range(2) / (0) of d_grads there while the rest of the
+ * backward pass runs; ranges (1) and (3) follow after the call.  reserve_sms: SMs the cooperative persistent recurrent
+ * kernels leave free so that the collective's few CTAs are never queued behind them (0 = use every SM).
+ * fsmg_param_range: [begin, end) element ranges of the flat buffers: 0 = embedding, 1 = LSTM kernels + biases,
+ * 2 = softmax_w + softmax_b, 3 = the FSMG_GRAD_EXTRA scalars (gradient buffer only). */
+int fsmg_set_stage_events(fsmg_handle* h, void* ev_softmax_grads, void* ev_embedding_grads, int32_t reserve_sms);
+int fsmg_param_range(const fsmg_handle* h, int32_t which, int64_t* begin, int64_t* end);
+
 /* clip_by_global_norm + Adam + exponential_decay + global_step++ (lstm_baseline.py:77-87) on the
  * (already reduced) d_grads; refreshes the fp16 operand copies.  `step` = global_step before
  * this update.  d_out_norm (1 float, may be NULL) receives the global norm. */
