@@ -104,10 +104,12 @@ class Engine:
     AR_CTAS = 4      # CTAs of the side communicator's kernels = SMs the persistent recurrent kernels leave free
 
     def _setup_overlapped_allreduce(self) -> None:
-        """The flat gradient buffer is reduced in slices as they become final (stage events recorded inside the library's
-        CUDA graph): softmax_w|softmax_b after the projection backward and the embedding after its GEMM — both on a side
-        stream through a communicator limited to AR_CTAS CTAs, while the recurrent backward (which leaves AR_CTAS SMs free)
-        and the kernel-gradient GEMMs run — then only the LSTM kernels/biases and the 8 scalars after the call."""
+        """The softmax_w | softmax_b slice of the flat gradient buffer (41 % of it at configs[1]) is final when the projection
+        backward ends, ~3 ms before the step does: it is all-reduced from a stage event (recorded inside the library's CUDA
+        graph) on a side stream, through a communicator limited to AR_CTAS CTAs that fit the SMs the persistent recurrent
+        kernels leave free.  Embedding | LSTM kernels | biases (one contiguous range) and the 8 scalars follow after the call at
+        full width.  Measured on 8 B200 (profiles/r2_optimization_log.md): also reducing the embedding slice on the 4-CTA
+        side communicator from a second event was slower than reducing it at full width afterwards."""
         import torch.distributed as dist
         try:
             opts = dist.ProcessGroupNCCL.Options()
@@ -125,7 +127,7 @@ class Engine:
         self._ev_soft, self._ev_emb = torch.cuda.Event(), torch.cuda.Event()
         for ev in (self._ev_soft, self._ev_emb):
             ev.record(torch.cuda.current_stream(self.device))     # materialises the cudaEvent_t
-        _lib.check(self.lib.fsmg_set_stage_events(self.h, self._ev_soft.cuda_event, self._ev_emb.cuda_event, self.AR_CTAS))
+        _lib.check(self.lib.fsmg_set_stage_events(self.h, self._ev_soft.cuda_event, None, self.AR_CTAS))
         # warm both communicators up (lazy NCCL init would otherwise land inside the first step)
         probe = torch.zeros(8, device=self.device)
         dist.all_reduce(probe, group=self._pg_side)
@@ -140,13 +142,11 @@ class Engine:
             return
         main = torch.cuda.current_stream(self.device)
         g, (emb, rnn, soft, extra) = self.grads, self._ranges
+        assert emb[1] == rnn[0] and rnn[1] == soft[0] and soft[1] == extra[0]
         self._side.wait_event(self._ev_soft)
         with torch.cuda.stream(self._side):
             dist.all_reduce(g[soft[0]:soft[1]], group=self._pg_side)
-        self._side.wait_event(self._ev_emb)
-        with torch.cuda.stream(self._side):
-            dist.all_reduce(g[emb[0]:emb[1]], group=self._pg_side)
-        dist.all_reduce(g[rnn[0]:rnn[1]], group=self.pg)          # after the whole backward pass, on the caller's stream
+        dist.all_reduce(g[emb[0]:rnn[1]], group=self.pg)          # after the whole backward pass, on the caller's stream
         dist.all_reduce(g[extra[0]:extra[1]], group=self.pg)
         main.wait_stream(self._side)
 
