@@ -100,6 +100,25 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                  "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+// NW (4, 8 or 16) consecutive columns from the head of a 16-word buffer
+template <int NW>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&w)[16]) {
+    if constexpr (NW == 16) {
+        tmem_st16(taddr, w);
+    } else if constexpr (NW == 8) {
+        uint32_t w8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w8[e] = w[e];
+        tmem_st8(taddr, w8);
+    } else {
+        static_assert(NW == 4, "4, 8 or 16 columns");
+        uint32_t w4[4] = {w[0], w[1], w[2], w[3]};
+        tmem_st4(taddr, w4);
+    }
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 #define FSMG_TR(step, slot)                                                                      \
@@ -127,6 +146,9 @@ struct LstmParams {
     int row_offset;        // first sequence handled by this launch (batch slicing when N is large)
     int n_rows;            // sequences handled by this launch
     int rotate;            // walk the K chunks in an order rotated per loader (FSMG_LSTM_ROT bit 0: backward, bit 1: forward)
+    int ks;                // pair + split backward: 64-column K chunks (TMA boxes) per ring stage = per full/empty barrier round trip
+    int box_pitch;         // bytes between the boxes of one stage (box rows x 128 B rounded to the 1024-B swizzle atom)
+    int alt;               // backward: K chunks alternate between two TMEM accumulators (breaks the dependent-accumulate chain of small MMAs)
 };
 
 // first element of the hoisted pre-activation row of token (t, row): direct, or through the per-word table
@@ -503,13 +525,17 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     while (ld_acquire(counter) < need) { }
                     if (hs_ == 0) FSMG_TR(t, 0);
                     fence_proxy_async_all();
-                    for (int kc = 0; kc < KC; ++kc) {
-                        // K chunks in an order rotated by the CTA's slice index: the C CTAs of a group read the same rows, and in
-                        // lock step they would all hit the same L2 lines at the same moment
-                        const int kcr = (kc + (p.rotate ? j : 0)) % KC;
+                    // K chunks in an order rotated by the CTA's slice index: the C CTAs of a group read the same rows, and in
+                    // lock step they would all hit the same L2 lines at the same moment.  p.ks chunks (TMA boxes) per ring stage:
+                    // one full/empty barrier round trip of the MMA thread per p.ks x 4 MMAs
+                    int kcr = (p.rotate ? j : 0) % KC;
+                    for (int kb = 0; kb < KC; kb += p.ks) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], box_bytes);
-                        tma_load_3d(sA + stage * STAGE_BYTES, &map_h, kcr * 64, group_row0 + hs_ * hr, t - 1, &full_bar[stage]);
+                        mbar_expect_tx(&full_bar[stage], p.ks * box_bytes);
+                        for (int i = 0; i < p.ks; ++i) {
+                            tma_load_3d(sA + stage * STAGE_BYTES + i * p.box_pitch, &map_h, kcr * 64, group_row0 + hs_ * hr, t - 1, &full_bar[stage]);
+                            if (++kcr == KC) kcr = 0;
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     if (hs_ == 0) FSMG_TR(t, 1);
@@ -523,6 +549,8 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             tc_fence_after();
             int stage = 0; uint32_t phase = 0;
             uint32_t pr_phase[4] = {0, 0, 0, 0};
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), 16, 1024);
+            const uint64_t a_step = (uint64_t)(p.box_pitch >> 4);
             for (int t = 1; t < p.T; ++t) {
                 for (int hs_ = 0; hs_ < 2; ++hs_) {
                     const int b = hs_ * 2 + (t & 1);
@@ -530,15 +558,22 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
                     pr_phase[b] ^= 1;
                     tc_fence_after();
                     const uint32_t d_buf = tmem_base + (uint32_t)(b * NCOL);
-                    for (int kc = 0; kc < KC; ++kc) {
+                    int kcr = (p.rotate ? j : 0) % KC;                    // same rotation as the producer
+                    for (int kb = 0; kb < KC; kb += p.ks) {
                         mbar_wait(&full_bar[stage], phase);
-                        if (kc == 0 && hs_ == 0) FSMG_TR(t, 2);
+                        if (kb == 0 && hs_ == 0) FSMG_TR(t, 2);
                         tc_fence_after();
-                        const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
-                        const uint32_t sb = smem_u32(sW + ((kc + (p.rotate ? j : 0)) % KC) * CHUNK_W);   // same rotation as the producer
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_f16(d_buf, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc, 1u);
+                        // descriptors built once per stage and advanced with 64-bit adds (start-address field = bytes >> 4)
+                        uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * STAGE_BYTES), 16, 1024);
+                        for (int i = 0; i < p.ks; ++i) {
+                            const uint64_t b_desc = b_desc0 + (uint64_t)(kcr * (CHUNK_W >> 4));
+                            umma_f16(d_buf, a_desc, b_desc, idesc, 1u);
+                            umma_f16(d_buf, a_desc + 2, b_desc + 2, idesc, 1u);
+                            umma_f16(d_buf, a_desc + 4, b_desc + 4, idesc, 1u);
+                            umma_f16(d_buf, a_desc + 6, b_desc + 6, idesc, 1u);
+                            a_desc += a_step;
+                            if (++kcr == KC) kcr = 0;
+                        }
                         umma_commit(&empty_bar[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -723,7 +758,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     const int n_loaders = p.ctas_per_group / (PAIR ? 2 : CLS);
     const int rot = p.rotate ? (((PAIR ? (j >> 1) : (j / CLS)) * KC) / (n_loaders > 0 ? n_loaders : 1)) % KC : 0;
     constexpr int STG_COLS = 5 * U;             // per row tile: gates (2U words) | c (U) | c_prev (U) | dh_out (U), staged by the epilogue warps
-    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS);
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS + (PAIR ? NQ * NCOL : 0));   // + the alternate accumulator
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
@@ -787,11 +822,14 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + ((kc + rot) % KC) * CHUNK_W);   // same rotation as the producer
                     if (PAIR) {
+                        // p.alt: odd K chunks accumulate into a second accumulator (spare TMEM columns); the epilogue adds the two
+                        const uint32_t d_acc = tmem_base + ((p.alt && (kc & 1)) ? (uint32_t)(NQ * NCOL + NQ * STG_COLS) : 0u);
+                        const int first_kc = (p.alt && (kc & 1)) ? 1 : 0;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t a_desc = make_smem_desc(sa + k * 32, 16, 1024);
                             const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
-                            umma_f16_2sm(tmem_base, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
+                            umma_f16_2sm(d_acc, a_desc, b_desc, idesc, (kc > first_kc || k > 0) ? 1u : 0u);
                         }
                         umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);
                     } else {
@@ -910,6 +948,11 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                         tmem_ld8(t_acc + u0, rr);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(rr[e]);
+                        if (PAIR && p.alt) {
+                            tmem_ld8(t_acc + (uint32_t)(NQ * NCOL + NQ * STG_COLS) + u0, rr);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[e] += __uint_as_float(rr[e]);
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
@@ -959,6 +1002,307 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     if (warp == 1) { if (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
+
+// =====================================================================================================
+// backward, second-generation pair kernel (default): lstm_bwd_pair2_kernel<U, NSUB>.
+//
+// What bounds the reverse-time recurrence (measured, profiles/r2_optimization_log.md).  The accumulator tile of a pair is only
+// 256 rows x 2U columns (all the resident weight slice allows), so one step is 4H/16 = 128 small tcgen05.mma (at configs[1]);
+// each costs ~85 cycles however it is issued — fetching the 128-row A tile from shared memory is not amortised over 64 output
+// columns — and every full/empty barrier round trip of the ring costs the issuing thread another ~190 cycles.  The first pair
+// kernel paid 128 x 90 + 32 x 190 = ~17.6k cycles per step for that, then ran the cell epilogue, the publish and the wait for the
+// other 15 CTAs of the group (~13k cycles) strictly afterwards.  This kernel
+//   * groups KS 64-column K chunks (TMA boxes) per ring stage: KS x fewer barrier round trips;
+//   * builds the UMMA descriptors once per stage and advances them with 64-bit adds;
+//   * writes the upstream gradient dh_out[t] INTO the accumulator before the step's MMAs start (every MMA accumulates), so the
+//     epilogue reads dh = dh_out + dgates_{t+1} Wh^T straight from TMEM;
+//   * NSUB = 1: splits a row's U units over two threads (16 epilogue warps = unit slice of the pair x unit half x TMEM lane
+//     quadrant), halving the dependent epilogue chain; all cell operands (gates, c, c_prev) are prefetched into spare TMEM columns;
+//   * publishes per warp (the group counter counts warps): no CTA-wide barrier before the release.
+//   * NSUB = 2 (FSMG_LSTM_BSPLIT=2): additionally cuts the group's rows into two sub-groups that the producer and the MMA thread
+//     serve alternately (one sub-group's epilogue / exchange hides behind the other's MMAs).  It doubles the number of MMAs per
+//     step — the bound resource — and measured slower than NSUB = 1 wherever the group has more than a few rows.
+// =====================================================================================================
+constexpr int LSTM_BSPLIT_THREADS = 64 + 512;
+constexpr int LSTM_BSPLIT_MAX_STAGES = 16;
+constexpr int LSTM_BSPLIT_BAR_BYTES = 512;
+
+template <int U, int NSUB>
+__global__ void __launch_bounds__(LSTM_BSPLIT_THREADS, 1)
+lstm_bwd_pair2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dg, LstmParams p) {
+    constexpr int CHUNK_W = U * 128;
+    constexpr int UH = NSUB == 1 ? U / 2 : U;   // units per epilogue thread
+    constexpr int ACC_COLS = 2 * U;             // one sub-group: both unit slices of the pair
+    constexpr bool STAGE_CPREV = NSUB == 1;     // c_{t-1} staged in TMEM too (NSUB = 2 has no columns left: read from L2)
+    constexpr int STG_COLS = (STAGE_CPREV ? 4 : 3) * UH;   // per epilogue quartet: gates (2 UH words) | c (UH) [| c_prev (UH)]
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NSUB * ACC_COLS + 4 * STG_COLS);
+    static_assert(NSUB * ACC_COLS + 4 * STG_COLS <= 512, "TMEM budget");
+    static_assert(UH % 8 == 0, "epilogue works on 8-unit chunks");
+    constexpr int WARPS_PER_SUB = 16 / NSUB;    // epilogue warps of one CTA that belong to one sub-group
+    const int KC = (4 * p.H) / 64;
+    const int W_BYTES = KC * CHUNK_W;
+    const int STAGES = p.stages;
+    const int STAGE_BYTES = p.stage_bytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem;
+    uint8_t* sA = sW + W_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LSTM_MAX_DYN - 1024 - LSTM_BSPLIT_BAR_BYTES);
+    uint64_t* full_bar = bars;                          // [16]
+    uint64_t* empty_bar = bars + LSTM_BSPLIT_MAX_STAGES;   // [16]
+    uint64_t* w_bar = bars + 2 * LSTM_BSPLIT_MAX_STAGES;
+    uint64_t* tmem_full = w_bar + 1;                    // [2] per sub-group
+    uint64_t* pre_ready = w_bar + 3;                    // [2] per sub-group (leader only): dh_out of the next step is staged in the accumulator
+    uint64_t* peer_w = w_bar + 5;                       // leader only: the peer's weight slice is resident
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x / p.ctas_per_group, j = blockIdx.x % p.ctas_per_group;
+    const int prank = (int)cluster_ctarank();
+    const int group_row0 = p.row_offset + g * p.rows_per_group;
+    const int group_rows = min(p.rows_per_group, p.row_offset + p.n_rows - group_row0);
+    const int hr = p.box_rows;                          // rows per (sub-group, CTA): multiple of 8, <= 128
+    const int n_loaders = p.ctas_per_group / 2;
+    const int rot = p.rotate ? (((j >> 1) * KC) / (n_loaders > 0 ? n_loaders : 1)) % KC : 0;
+    const int pub_per_step = p.ctas_per_group;          // one release per (CTA, sub-group) and step
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_w);
+        tma_prefetch_desc(&map_dg);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(w_bar, 1);
+        mbar_init(&tmem_full[0], 1);
+        mbar_init(&tmem_full[1], 1);
+        mbar_init(&pre_ready[0], 2 * WARPS_PER_SUB);    // the sub-group's epilogue warps of both CTAs of the pair
+        mbar_init(&pre_ready[1], 2 * WARPS_PER_SUB);
+        mbar_init(peer_w, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, (uint32_t)W_BYTES);
+            for (int kc = 0; kc < KC; ++kc) tma_load_2d(sW + kc * CHUNK_W, &map_w, kc * 64, j * U, w_bar);
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t box_bytes = (uint32_t)hr * 128u;
+            for (int s = 1; s < p.T; ++s) {             // s-th processed step handles t = T-1-s and needs dgates_{t+1}
+                const int t = p.T - 1 - s;
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    const int* counter = p.counters + 2 * g + sub;
+                    while (ld_acquire(counter) < pub_per_step * s) { }
+                    if (sub == 0) FSMG_TR(s, 0);
+                    fence_proxy_async_all();
+                    const int row0 = group_row0 + sub * 2 * hr + prank * hr;
+                    int kcr = rot;
+                    for (int kb = 0; kb < KC; kb += p.ks) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        if (prank == 0) mbar_expect_tx(&full_bar[stage], 2 * p.ks * box_bytes);
+                        for (int i = 0; i < p.ks; ++i) {
+                            tma_load_3d_2sm(sA + stage * STAGE_BYTES + i * p.box_pitch, &map_dg, kcr * 64, row0, t + 1, &full_bar[stage]);
+                            if (++kcr == KC) kcr = 0;
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    if (sub == 0) FSMG_TR(s, 1);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && prank == 1) {
+            mbar_wait(w_bar, 0);
+            mbar_arrive_remote_release(peer_w, 0);
+        } else if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_m(256, 2 * U);
+            mbar_wait(w_bar, 0);
+            mbar_wait(peer_w, 0);
+            tc_fence_after();
+            int stage = 0; uint32_t phase = 0;
+            uint32_t pr_phase[2] = {0, 0};
+            const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), 16, 1024);
+            const uint64_t a_step = (uint64_t)(p.box_pitch >> 4);
+            for (int s = 1; s < p.T; ++s) {
+                for (int sub = 0; sub < NSUB; ++sub) {
+                    mbar_wait(&pre_ready[sub], pr_phase[sub]);      // dh_out[t] sits in the accumulator: every MMA accumulates
+                    pr_phase[sub] ^= 1;
+                    tc_fence_after();
+                    const uint32_t d_buf = tmem_base + (uint32_t)(sub * ACC_COLS);
+                    int kcr = rot;
+                    for (int kb = 0; kb < KC; kb += p.ks) {
+                        mbar_wait(&full_bar[stage], phase);
+                        if (kb == 0 && sub == 0) FSMG_TR(s, 2);
+                        tc_fence_after();
+                        // descriptors: built once per stage, advanced with plain 64-bit adds (start-address field = bytes >> 4)
+                        uint64_t a_desc = make_smem_desc(smem_u32(sA + stage * STAGE_BYTES), 16, 1024);
+                        for (int i = 0; i < p.ks; ++i) {
+                            const uint64_t b_desc = b_desc0 + (uint64_t)(kcr * (CHUNK_W >> 4));
+                            umma_f16_2sm(d_buf, a_desc, b_desc, idesc, 1u);
+                            umma_f16_2sm(d_buf, a_desc + 2, b_desc + 2, idesc, 1u);
+                            umma_f16_2sm(d_buf, a_desc + 4, b_desc + 4, idesc, 1u);
+                            umma_f16_2sm(d_buf, a_desc + 6, b_desc + 6, idesc, 1u);
+                            a_desc += a_step;
+                            if (++kcr == KC) kcr = 0;
+                        }
+                        umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_2sm_mc(&tmem_full[sub], (uint16_t)0x3);
+                    if (sub == 0) FSMG_TR(s, 3);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 16 warps x 32 lanes; thread <-> one row (TMEM lane), UH units.
+        //   NSUB = 1: quartet qd -> unit slice of the pair (qd & 1), unit half (qd >> 1)
+        //   NSUB = 2: quartet qd -> sub-group (qd >> 1), unit slice of the pair (qd & 1)
+        const int quad = warp & 3;
+        const int qd = (warp - 2) >> 2;
+        const int sub = NSUB == 1 ? 0 : qd >> 1;
+        const int us = qd & 1;
+        const int ucol = ((j & ~1) + us) * U + (NSUB == 1 ? (qd >> 1) * UH : 0);   // first hidden unit of this thread
+        const int row_base = group_row0 + sub * 2 * hr + prank * hr;
+        const int rows = max(0, min(hr, group_rows - sub * 2 * hr - prank * hr));
+        const int lrow = quad * 32 + lane;
+        const bool ok = lrow < rows;
+        const bool warp_active = quad * 32 < rows;          // warp-uniform: quadrants without rows only keep the barriers in step
+        int* counter = p.counters + 2 * g + sub;
+        const bool tracer = (qd == 0 && quad == 0 && lane == 0);
+        const uint32_t t_acc = tmem_base + (uint32_t)(sub * ACC_COLS + us * U + (NSUB == 1 ? (qd >> 1) * UH : 0)) + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_stg = tmem_base + (uint32_t)(NSUB * ACC_COLS + qd * STG_COLS) + ((uint32_t)(quad * 32) << 16);
+        float dc_state[UH];
+#pragma unroll
+        for (int u = 0; u < UH; ++u) dc_state[u] = 0.0f;
+        uint32_t tf_phase = 0;
+        // forward stash of step t (gates, c [, c_prev]) -> staging columns, upstream gradient dh_out[t] -> accumulator; 16 words per store
+        auto stage_step = [&](int t) {
+            const int64_t r = (int64_t)t * p.N + row_base + lrow;
+            const __half* gin = p.gates + r * p.G4p + ucol;
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {                   // gate q: UH halves = UH/2 words
+#pragma unroll
+                for (int e0 = 0; e0 < UH / 2; e0 += 16) {
+                    constexpr int NW = UH / 2 < 16 ? UH / 2 : 16;
+#pragma unroll
+                    for (int e = 0; e < NW; e += 4) {
+                        const uint4 v = ok ? __ldcs(reinterpret_cast<const uint4*>(gin + q * p.H + 2 * (e0 + e))) : make_uint4(0, 0, 0, 0);
+                        w[e] = v.x; w[e + 1] = v.y; w[e + 2] = v.z; w[e + 3] = v.w;
+                    }
+                    tmem_st_n<NW>(t_stg + q * (UH / 2) + e0, w);
+                }
+            }
+#pragma unroll
+            for (int which = 0; which < (STAGE_CPREV ? 3 : 2); ++which) {
+                const float* src = which == 0 ? p.c + r * p.H + ucol : which == 1 ? p.dh_out + r * p.H + ucol : p.c + (r - p.N) * p.H + ucol;
+                const bool have = ok && !(which == 2 && t == 0);
+                const uint32_t dst = which == 0 ? t_stg + 2 * UH : which == 1 ? t_acc : t_stg + 3 * UH;
+#pragma unroll
+                for (int e0 = 0; e0 < UH; e0 += 16) {
+                    constexpr int NW = UH < 16 ? UH : 16;
+#pragma unroll
+                    for (int e = 0; e < NW; e += 4) {
+                        const float4 v = have ? __ldcs(reinterpret_cast<const float4*>(src + e0 + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        w[e] = __float_as_uint(v.x); w[e + 1] = __float_as_uint(v.y); w[e + 2] = __float_as_uint(v.z); w[e + 3] = __float_as_uint(v.w);
+                    }
+                    tmem_st_n<NW>(dst + e0, w);
+                }
+            }
+            tmem_st_wait();
+        };
+        if (warp_active) stage_step(p.T - 1);
+        for (int s = 0; s < p.T; ++s) {
+            const int t = p.T - 1 - s;
+            const int64_t r = (int64_t)t * p.N + row_base + lrow;
+            const bool have_prev = ok && t > 0;
+            const float* cprev = p.c + (r - p.N) * p.H + ucol;         // NSUB = 2 only: c_{t-1} from L2 (prefetched one step ago)
+            float4 nx0 = make_float4(0.f, 0.f, 0.f, 0.f), nx1 = nx0;
+            if (!STAGE_CPREV && have_prev) { nx0 = __ldg(reinterpret_cast<const float4*>(cprev)); nx1 = __ldg(reinterpret_cast<const float4*>(cprev + 4)); }
+            if (s > 0) {
+                mbar_wait(&tmem_full[sub], tf_phase);
+                tf_phase ^= 1;
+                tc_fence_after();
+            }
+            if (tracer) FSMG_TR(s, 5);
+            if (warp_active) {
+                __half* dgo = p.dgates + r * p.G4p + ucol;
+#pragma unroll
+                for (int u0 = 0; u0 < UH; u0 += 8) {
+                    uint32_t dh[8], gw[4][4], cw[8], pw[8];
+                    if constexpr (!STAGE_CPREV) {
+                        pw[0] = __float_as_uint(nx0.x); pw[1] = __float_as_uint(nx0.y); pw[2] = __float_as_uint(nx0.z); pw[3] = __float_as_uint(nx0.w);
+                        pw[4] = __float_as_uint(nx1.x); pw[5] = __float_as_uint(nx1.y); pw[6] = __float_as_uint(nx1.z); pw[7] = __float_as_uint(nx1.w);
+                        if (u0 + 8 < UH && have_prev) {
+                            nx0 = __ldg(reinterpret_cast<const float4*>(cprev + u0 + 8));
+                            nx1 = __ldg(reinterpret_cast<const float4*>(cprev + u0 + 12));
+                        }
+                    }
+                    tmem_ld8(t_acc + u0, dh);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) tmem_ld4(t_stg + q * (UH / 2) + u0 / 2, gw[q]);
+                    tmem_ld8(t_stg + 2 * UH + u0, cw);
+                    if constexpr (STAGE_CPREV) tmem_ld8(t_stg + 3 * UH + u0, pw);
+                    tmem_ld_wait();
+                    if (ok) {
+                        __align__(16) __half dq[4][8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const __half2 hi2 = *reinterpret_cast<const __half2*>(&gw[0][e >> 1]);
+                            const __half2 hj2 = *reinterpret_cast<const __half2*>(&gw[1][e >> 1]);
+                            const __half2 hf2 = *reinterpret_cast<const __half2*>(&gw[2][e >> 1]);
+                            const __half2 ho2 = *reinterpret_cast<const __half2*>(&gw[3][e >> 1]);
+                            const float i_ = (e & 1) ? __high2float(hi2) : __low2float(hi2);
+                            const float j_ = (e & 1) ? __high2float(hj2) : __low2float(hj2);
+                            const float f_ = (e & 1) ? __high2float(hf2) : __low2float(hf2);
+                            const float o_ = (e & 1) ? __high2float(ho2) : __low2float(ho2);
+                            const float dhv = __uint_as_float(dh[e]);              // dh_out[t] + dgates_{t+1} * Wh^T (accumulated in TMEM)
+                            const float tcv = tanh_fast(__uint_as_float(cw[e]));
+                            const float d_o = dhv * tcv;
+                            const float dc = dhv * o_ * (1.0f - tcv * tcv) + dc_state[u0 + e];
+                            dq[0][e] = __float2half_rn(dc * j_ * i_ * (1.0f - i_));
+                            dq[1][e] = __float2half_rn(dc * i_ * (1.0f - j_ * j_));
+                            dq[2][e] = __float2half_rn(dc * __uint_as_float(pw[e]) * f_ * (1.0f - f_));
+                            dq[3][e] = __float2half_rn(d_o * o_ * (1.0f - o_));
+                            dc_state[u0 + e] = dc * f_;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(dgo + q * p.H + u0) = *reinterpret_cast<uint4*>(dq[q]);
+                    }
+                }
+            }
+            // publish: barrier among the sub-group's epilogue warps, then ONE gpu-scope release per (CTA, sub-group) — it is cumulative over
+            // the dgates stores the other warps made before the barrier.  (A release per warp, 16 fences per CTA and step, measured
+            // slower: the group's counter completed 7-10k cycles after the first warp's publish instead of 3k.)
+            tc_fence_before();
+            if (tracer) FSMG_TR(s, 6);
+            named_bar_sync(1 + sub, 32 * WARPS_PER_SUB);
+            if (qd == (NSUB == 1 ? 0 : 2 * sub) && quad == 0 && lane == 0) { if (tracer) FSMG_TR(s, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(s, 8); }
+            if (s + 1 < p.T) {
+                // stage the next processed step while the exchange is in flight (and, NSUB = 2, the other sub-group's MMAs run)
+                if (warp_active) stage_step(t - 1);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (prank == 1) mbar_arrive_remote(&pre_ready[sub], 0); else mbar_arrive(&pre_ready[sub]); }
+                if (t > 1 && ok) {   // and pull the step after that towards L2
+                    const int64_t rn = r - 2 * (int64_t)p.N;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) prefetch_l2(p.gates + rn * p.G4p + q * p.H + ucol);
+                    prefetch_l2(p.dh_out + rn * p.H + ucol);
+                    if (t > 2 || !STAGE_CPREV) prefetch_l2(p.c + (rn - (STAGE_CPREV ? p.N : 0)) * p.H + ucol);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+}
+
 }  // namespace tc
 
 // =====================================================================================================
@@ -973,6 +1317,19 @@ static inline void lstm_ring(int w_bytes, int box_rows, int mt, int* stage_bytes
     int n = (avail - window) / sb + 1;
     if (n > 8) n = 8;
     if (n < 2) { sb = window; n = avail / window; }
+    *stage_bytes = sb;
+    *stages = n;
+}
+
+// pair + split backward: 16-deep ring of the narrow sub-group boxes, barrier block of LSTM_BSPLIT_BAR_BYTES
+static inline void lstm_ring_bsplit(int w_bytes, int box_rows, int ks, int* box_pitch, int* stage_bytes, int* stages) {
+    const int avail = tc::LSTM_MAX_DYN - 1024 - tc::LSTM_BSPLIT_BAR_BYTES - w_bytes;
+    const int pitch = (int)round_up((int64_t)box_rows * 128, 1024);
+    const int window = 128 * 128;       // the UMMA descriptors address a full 128-row tile from every box base
+    const int sb = ks * pitch;
+    int n = (avail - (window - pitch)) / sb;
+    if (n > tc::LSTM_BSPLIT_MAX_STAGES) n = tc::LSTM_BSPLIT_MAX_STAGES;
+    *box_pitch = pitch;
     *stage_bytes = sb;
     *stages = n;
 }
@@ -994,14 +1351,15 @@ static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, bool want_pai
     pl.U = U;
     pl.C = H / U;
     int cls = cls_req >= 0 ? cls_req : c.lstm_cluster;
-    if (cls != 1 && cls != 2 && cls != 4) cls = 1;
+    if (cls != 1 && cls != 2 && cls != 4 && cls != 8) cls = 1;
     while (cls > 1 && (pl.C % cls) != 0) cls >>= 1;
     pl.cls = cls;
     // clusters of 4 cannot use every SM (GPC sizes are not multiples of 4): 132 co-resident CTAs at most
     // lstm_reserve_sms: every CTA of these cooperative kernels must be resident at once; the SMs left free host the (few-CTA) NCCL
     // kernels of a gradient all-reduce that overlaps the backward pass (fsmg_set_stage_events)
     const int usable = c.num_sms - c.lstm_reserve_sms > 0 ? c.num_sms - c.lstm_reserve_sms : c.num_sms;
-    const int sms = cls == 4 ? (usable < 132 ? usable / 4 * 4 : 132) : usable;
+    // clusters of 8: two per GPC (GPCs hold 16..20 SMs) -> 128 co-resident CTAs
+    const int sms = cls == 8 ? (usable < 128 ? usable / 8 * 8 : 128) : cls == 4 ? (usable < 132 ? usable / 4 * 4 : 132) : usable;
     int gmax = sms / pl.C;
     if (gmax < 1) return pl;
     int mg = cdiv(N, gmax);
@@ -1067,11 +1425,13 @@ static inline int lstm_launch(K kernel, int grid, int threads, int cls, int smem
         if (pl.pair && (ALLOW_PAIR)) {                                                                            \
             if (pl.U == 32) FSMG_LSTM_GO(KERNEL, 32, 1, 1, true); else FSMG_LSTM_GO(KERNEL, 16, 1, 1, true);      \
         } else if (pl.U == 32 && pl.MT == 2) {                                                                    \
-            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 2, 4, false);                                               \
+            if (pl.cls == 8) FSMG_LSTM_GO(KERNEL, 32, 2, 8, false);                                               \
+            else if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 2, 4, false);                                          \
             else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 32, 2, 2, false);                                          \
             else FSMG_LSTM_GO(KERNEL, 32, 2, 1, false);                                                           \
         } else if (pl.U == 32) {                                                                                  \
-            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 1, 4, false);                                               \
+            if (pl.cls == 8) FSMG_LSTM_GO(KERNEL, 32, 1, 8, false);                                               \
+            else if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 1, 4, false);                                          \
             else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 32, 1, 2, false);                                          \
             else FSMG_LSTM_GO(KERNEL, 32, 1, 1, false);                                                           \
         } else if (pl.MT == 2) {                                                                                  \
@@ -1143,7 +1503,16 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const int32_t
         if (split) {
             // two independent halves per group (own counters: 2 per group), one CTA per (group, unit slice)
             p.box_rows = half_rows;
-            lstm_ring(w_bytes, half_rows, 1, &p.stage_bytes, &p.stages);
+            int ks = c.lstm_fks;
+            while (ks > 1 && ((H / 64) % ks) != 0) ks >>= 1;
+            for (;; ks >>= 1) {      // ring of (ks boxes)-stages: at least 2 stages, at most 8 (barrier array)
+                p.box_pitch = (int)round_up((int64_t)half_rows * 128, 1024);
+                p.stage_bytes = ks * p.box_pitch;
+                p.stages = (tc::LSTM_MAX_DYN - 1024 - 256 - w_bytes - (128 * 128 - p.box_pitch)) / p.stage_bytes;
+                if (p.stages > 8) p.stages = 8;
+                if (p.stages >= 2 || ks == 1) break;
+            }
+            p.ks = ks;
             if (pl.U == 32) rc = lstm_launch(tc::lstm_fwd_split_kernel<32>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
             else rc = lstm_launch(tc::lstm_fwd_split_kernel<16>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
         } else {
@@ -1163,7 +1532,21 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
     CUtensorMap mw, md;
     int rc = make_map_f16(c, &mw, Wh_rows, (uint64_t)4 * H, (uint64_t)H, (uint64_t)G4p, 64, (uint32_t)pl.U);
     if (rc) return rc;
-    rc = make_map_f16_3d(c, &md, dgates, (uint64_t)4 * H, (uint64_t)N, (uint64_t)T, (uint64_t)G4p, (uint64_t)N * G4p, 64, (uint32_t)pl.box_rows);
+    // second-generation pair kernel (default): lstm_bwd_pair2_kernel<U, NSUB>; FSMG_LSTM_BSPLIT = 0 old pair kernel, 1 (default) NSUB = 1,
+    // 2 NSUB = 2 (two alternating sub-groups per pair)
+    // auto (measured, profiles/r2_optimization_log.md): two alternating sub-groups pay off only when a group holds many rows
+    // (configs[1]: 160 rows per group, 2.16 -> 2.05 ms); with few rows (configs[2]: 24) they only double the MMA count (3.5 -> 5.5 ms)
+    const int mode = c.lstm_bsplit >= 0 ? c.lstm_bsplit : (pl.rows_per_group > 64 ? 2 : 1);
+    const int nsub = mode == 2 ? 2 : 1;
+    const int sub_rows = (int)round_up(cdiv(pl.rows_per_group, 2 * nsub), 8);
+    int bs_stage = 0, bs_stages = 0, bs_pitch = 0;
+    int ks = c.lstm_ks > 0 ? c.lstm_ks : (sub_rows <= 32 ? 8 : 4);
+    while (ks > 1 && ((4 * H / 64) % ks) != 0) ks >>= 1;
+    lstm_ring_bsplit((4 * H / 64) * pl.U * 128, sub_rows, ks, &bs_pitch, &bs_stage, &bs_stages);
+    while (bs_stages < 2 && ks > 1) { ks >>= 1; lstm_ring_bsplit((4 * H / 64) * pl.U * 128, sub_rows, ks, &bs_pitch, &bs_stage, &bs_stages); }
+    const bool bsplit = mode != 0 && pl.pair && pl.rows_per_group >= 16 && bs_stages >= 2 && sub_rows <= 128;
+    rc = make_map_f16_3d(c, &md, dgates, (uint64_t)4 * H, (uint64_t)N, (uint64_t)T, (uint64_t)G4p, (uint64_t)N * G4p, 64,
+                         (uint32_t)(bsplit ? sub_rows : pl.box_rows));
     if (rc) return rc;
     for (int off = 0; off < N; off += pl.rows_per_launch) {
         int n_rows = N - off < pl.rows_per_launch ? N - off : pl.rows_per_launch;
@@ -1171,6 +1554,7 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
         tc::LstmParams p;
         memset(&p, 0, sizeof p);
+        p.alt = c.lstm_alt;
         p.dh_out = dh_out; p.dgates = dgates; p.gates = const_cast<__half*>(gates); p.c = const_cast<float*>(cbuf); p.counters = c.counters; p.rotate = (c.lstm_rot & 1) != 0;
         p.N = N; p.T = T; p.H = H; p.Hp = 0; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;
@@ -1180,8 +1564,20 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         const CUtensorMap& mx = md;
         const bool trace = getenv("FSMG_TRACE") != nullptr && c.trace != nullptr;
         if (trace) { cudaMemsetAsync(c.trace, 0, 8 * 16 * sizeof(long long), s); p.trace = c.trace; }
-        FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc, true);
-        if (trace && !rc) lstm_trace_dump(c, "lstm_bwd_persistent", s);
+        if (bsplit) {
+            p.box_rows = sub_rows;
+            p.stage_bytes = bs_stage;
+            p.stages = bs_stages;
+            p.ks = ks;
+            p.box_pitch = bs_pitch;
+            if (pl.U == 32 && nsub == 1) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 1>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else if (pl.U == 32) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 2>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else if (nsub == 1) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<16, 1>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else rc = lstm_launch(tc::lstm_bwd_pair2_kernel<16, 2>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+        } else {
+            FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc, true);
+        }
+        if (trace && !rc) lstm_trace_dump(c, bsplit ? (nsub == 2 ? "lstm_bwd_pair2<NSUB=2>" : "lstm_bwd_pair2<NSUB=1>") : "lstm_bwd_persistent", s);
         if (rc) return rc;
     }
     return 0;
