@@ -1069,7 +1069,6 @@ struct TcContext {
     int lstm_bsplit = -1;      // backward recurrent kernel (FSMG_LSTM_BSPLIT): -1 auto, 0 first-generation pair kernel, 1 lstm_bwd_pair2<NSUB=1>, 2 <NSUB=2>
     int lstm_ks = 0;           // backward pair2 kernel: K chunks per ring stage (FSMG_LSTM_KS = 1, 2, 4, 8; 0 = auto)
     int lstm_fks = 4;          // forward split kernel: K chunks per ring stage (FSMG_LSTM_FKS = 1, 2, 4)
-    int lstm_alt = 0;          // backward pair kernel: alternate K chunks between two accumulators (FSMG_LSTM_ALT=1)
     int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
     int lstm_reserve_sms = 0;  // SMs the persistent recurrent kernels leave free (for the NCCL kernels of an overlapped gradient all-reduce)
@@ -1107,8 +1106,6 @@ static inline int tc_init(TcContext& c) {
     if (envks && atoi(envks) > 0) c.lstm_ks = atoi(envks);
     const char* envfks = getenv("FSMG_LSTM_FKS");
     if (envfks && atoi(envfks) > 0) c.lstm_fks = atoi(envfks);
-    const char* envalt = getenv("FSMG_LSTM_ALT");
-    if (envalt) c.lstm_alt = atoi(envalt);
     const char* envr = getenv("FSMG_LSTM_ROT");
     if (envr) c.lstm_rot = atoi(envr);
     const char* envst = getenv("FSMG_STRIP");

@@ -148,7 +148,6 @@ struct LstmParams {
     int rotate;            // walk the K chunks in an order rotated per loader (FSMG_LSTM_ROT bit 0: backward, bit 1: forward)
     int ks;                // pair + split backward: 64-column K chunks (TMA boxes) per ring stage = per full/empty barrier round trip
     int box_pitch;         // bytes between the boxes of one stage (box rows x 128 B rounded to the 1024-B swizzle atom)
-    int alt;               // backward: K chunks alternate between two TMEM accumulators (breaks the dependent-accumulate chain of small MMAs)
 };
 
 // first element of the hoisted pre-activation row of token (t, row): direct, or through the per-word table
@@ -758,7 +757,7 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
     const int n_loaders = p.ctas_per_group / (PAIR ? 2 : CLS);
     const int rot = p.rotate ? (((PAIR ? (j >> 1) : (j / CLS)) * KC) / (n_loaders > 0 ? n_loaders : 1)) % KC : 0;
     constexpr int STG_COLS = 5 * U;             // per row tile: gates (2U words) | c (U) | c_prev (U) | dh_out (U), staged by the epilogue warps
-    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS + (PAIR ? NQ * NCOL : 0));   // + the alternate accumulator
+    constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NQ * NCOL + NQ * STG_COLS);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_w);
@@ -822,14 +821,11 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                     const uint32_t sa = smem_u32(sA + stage * STAGE_BYTES);
                     const uint32_t sb = smem_u32(sW + ((kc + rot) % KC) * CHUNK_W);   // same rotation as the producer
                     if (PAIR) {
-                        // p.alt: odd K chunks accumulate into a second accumulator (spare TMEM columns); the epilogue adds the two
-                        const uint32_t d_acc = tmem_base + ((p.alt && (kc & 1)) ? (uint32_t)(NQ * NCOL + NQ * STG_COLS) : 0u);
-                        const int first_kc = (p.alt && (kc & 1)) ? 1 : 0;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const uint64_t a_desc = make_smem_desc(sa + k * 32, 16, 1024);
                             const uint64_t b_desc = make_smem_desc(sb + k * 32, 16, 1024);
-                            umma_f16_2sm(d_acc, a_desc, b_desc, idesc, (kc > first_kc || k > 0) ? 1u : 0u);
+                            umma_f16_2sm(tmem_base, a_desc, b_desc, idesc, (kc > 0 || k > 0) ? 1u : 0u);
                         }
                         umma_commit_2sm_mc(&empty_bar[stage], (uint16_t)0x3);
                     } else {
@@ -948,11 +944,6 @@ lstm_bwd_persistent_kernel(const __grid_constant__ CUtensorMap map_w, const __gr
                         tmem_ld8(t_acc + u0, rr);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = __uint_as_float(rr[e]);
-                        if (PAIR && p.alt) {
-                            tmem_ld8(t_acc + (uint32_t)(NQ * NCOL + NQ * STG_COLS) + u0, rr);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) acc[e] += __uint_as_float(rr[e]);
-                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
@@ -1351,15 +1342,14 @@ static inline LstmPlan lstm_plan(const TcContext& c, int N, int H, bool want_pai
     pl.U = U;
     pl.C = H / U;
     int cls = cls_req >= 0 ? cls_req : c.lstm_cluster;
-    if (cls != 1 && cls != 2 && cls != 4 && cls != 8) cls = 1;
+    if (cls != 1 && cls != 2 && cls != 4) cls = 1;
     while (cls > 1 && (pl.C % cls) != 0) cls >>= 1;
     pl.cls = cls;
     // clusters of 4 cannot use every SM (GPC sizes are not multiples of 4): 132 co-resident CTAs at most
     // lstm_reserve_sms: every CTA of these cooperative kernels must be resident at once; the SMs left free host the (few-CTA) NCCL
     // kernels of a gradient all-reduce that overlaps the backward pass (fsmg_set_stage_events)
     const int usable = c.num_sms - c.lstm_reserve_sms > 0 ? c.num_sms - c.lstm_reserve_sms : c.num_sms;
-    // clusters of 8: two per GPC (GPCs hold 16..20 SMs) -> 128 co-resident CTAs
-    const int sms = cls == 8 ? (usable < 128 ? usable / 8 * 8 : 128) : cls == 4 ? (usable < 132 ? usable / 4 * 4 : 132) : usable;
+    const int sms = cls == 4 ? (usable < 132 ? usable / 4 * 4 : 132) : usable;   // (clusters of 8 do not fit a cooperative launch at 227 KB/CTA)
     int gmax = sms / pl.C;
     if (gmax < 1) return pl;
     int mg = cdiv(N, gmax);
@@ -1425,13 +1415,11 @@ static inline int lstm_launch(K kernel, int grid, int threads, int cls, int smem
         if (pl.pair && (ALLOW_PAIR)) {                                                                            \
             if (pl.U == 32) FSMG_LSTM_GO(KERNEL, 32, 1, 1, true); else FSMG_LSTM_GO(KERNEL, 16, 1, 1, true);      \
         } else if (pl.U == 32 && pl.MT == 2) {                                                                    \
-            if (pl.cls == 8) FSMG_LSTM_GO(KERNEL, 32, 2, 8, false);                                               \
-            else if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 2, 4, false);                                          \
+            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 2, 4, false);                                               \
             else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 32, 2, 2, false);                                          \
             else FSMG_LSTM_GO(KERNEL, 32, 2, 1, false);                                                           \
         } else if (pl.U == 32) {                                                                                  \
-            if (pl.cls == 8) FSMG_LSTM_GO(KERNEL, 32, 1, 8, false);                                               \
-            else if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 1, 4, false);                                          \
+            if (pl.cls == 4) FSMG_LSTM_GO(KERNEL, 32, 1, 4, false);                                               \
             else if (pl.cls == 2) FSMG_LSTM_GO(KERNEL, 32, 1, 2, false);                                          \
             else FSMG_LSTM_GO(KERNEL, 32, 1, 1, false);                                                           \
         } else if (pl.MT == 2) {                                                                                  \
@@ -1554,7 +1542,6 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
         FSMG_CUDA_OK(cudaMemsetAsync(c.counters, 0, sizeof(int) * 256, s));
         tc::LstmParams p;
         memset(&p, 0, sizeof p);
-        p.alt = c.lstm_alt;
         p.dh_out = dh_out; p.dgates = dgates; p.gates = const_cast<__half*>(gates); p.c = const_cast<float*>(cbuf); p.counters = c.counters; p.rotate = (c.lstm_rot & 1) != 0;
         p.N = N; p.T = T; p.H = H; p.Hp = 0; p.G4p = G4p;
         p.ctas_per_group = pl.C; p.rows_per_group = pl.rows_per_group; p.box_rows = pl.box_rows; p.row_offset = off; p.n_rows = n_rows;

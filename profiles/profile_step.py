@@ -11,7 +11,7 @@ sys.path.insert(0, str(ROOT))
 import bench  # noqa: E402
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-w = bench.WORKLOADS["lyrics5shot_v10k_t128_h512"]
+w = bench.WORKLOADS[sys.argv[2] if len(sys.argv) > 2 else "lyrics5shot_v10k_t128_h512"]
 cfg = bench.model_config(w)
 from fsmg.engine import Engine  # noqa: E402
 
@@ -21,7 +21,7 @@ eng.init_params(1234)
 rng = np.random.RandomState(0)
 from data import synthetic as O  # noqa: E402
 
-tok = torch.from_numpy(O.synthetic_tokens(rng, (n, w["max_len"]), w["input_size"], "zipf")).cuda()
+tok = torch.from_numpy(O.synthetic_tokens(rng, (n, w["max_len"]), w["input_size"], w["kind"])).cuda()
 for _ in range(steps):
     eng.train_step_device(tok)
 torch.cuda.synchronize()
