@@ -15,5 +15,12 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:soft
     python profiles/profile_step.py 1 > $out/${tag}_ncu_softmax.log 2>&1
 FSMG_SAMPLE_GRAPH=0 timeout 900 ncu --set full --clock-control none --import-source on -k "regex:tc_gemm_kernel|sample_cell|argmax_rows" -s 9 -c 4 -f -o $out/${tag}_sample \
     python profiles/profile_sample.py 6 > $out/${tag}_ncu_sample.log 2>&1
-tail -2 $out/${tag}_ncu_*.log
+# the reports themselves exceed gpurun's 64 MiB return limit: summarise on the box, keep the raw-page CSV (one row per kernel), drop the reports
+for r in lstm lstm_midi gemm softmax sample; do
+  ncu -i $out/${tag}_$r.ncu-rep --page raw --csv > $out/${tag}_$r.raw.csv 2>/dev/null
+done
+python profiles/summarize_ncu.py $out/${tag}_gemm.ncu-rep $out/${tag}_lstm.ncu-rep $out/${tag}_softmax.ncu-rep $out/${tag}_lstm_midi.ncu-rep $out/${tag}_sample.ncu-rep > $out/${tag}_ncu_summary.md 2>&1
+python profiles/summarize_launches.py $out/${tag}_launches.csv > $out/${tag}_launches_summary.md 2>&1
+rm -f $out/${tag}_*.ncu-rep
+for f in $out/${tag}_ncu_*.log; do tail -n 2 $f; done
 ls -la $out | grep ${tag}_
