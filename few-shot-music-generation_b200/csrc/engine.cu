@@ -718,9 +718,14 @@ static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
             rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l - 1], 3 * h->Hp, h->KxT3[l], 3 * h->Hp, h->s_g, h->G4, a, nullptr, 0, 0, 1), false, false, s);
             if (rc) return rc;
         }
-        sample_cell_kernel<<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, l == 0 ? h->P0 : nullptr, h->G4, h->samp_ids,
-                                                                 l == 0 ? nullptr : h->params + h->layers[l].b_off, h->s_c[l], h->h3[l],
-                                                                 h->Hp, n, H);
+        if ((H & 3) == 0)
+            sample_cell_kernel<<<cdiv((int64_t)n * (H / 4), TB), TB, 0, s>>>(h->s_g, h->G4, l == 0 ? h->P0 : nullptr, h->G4, h->samp_ids,
+                                                                           l == 0 ? nullptr : h->params + h->layers[l].b_off, h->s_c[l],
+                                                                           h->h3[l], h->Hp, n, H);
+        else
+            sample_cell_scalar_kernel<<<cdiv((int64_t)n * H, TB), TB, 0, s>>>(h->s_g, h->G4, l == 0 ? h->P0 : nullptr, h->G4, h->samp_ids,
+                                                                            l == 0 ? nullptr : h->params + h->layers[l].b_off, h->s_c[l],
+                                                                            h->h3[l], h->Hp, n, H);
         LAUNCH_COUNT(h);
     }
     rc = gemm_f16(h, mk(n, h->V1, 3 * h->Hp, h->h3[h->L - 1], 3 * h->Hp, h->WsT3, 3 * h->Hp, h->s_logits2, h->Vp, a,

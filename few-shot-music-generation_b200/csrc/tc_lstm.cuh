@@ -148,6 +148,7 @@ struct LstmParams {
     int rotate;            // walk the K chunks in an order rotated per loader (FSMG_LSTM_ROT bit 0: backward, bit 1: forward)
     int ks;                // pair + split backward: 64-column K chunks (TMA boxes) per ring stage = per full/empty barrier round trip
     int box_pitch;         // bytes between the boxes of one stage (box rows x 128 B rounded to the 1024-B swizzle atom)
+    int pub_cta;           // forward split kernel: one release per (CTA, half) behind a named barrier instead of one per warp
 };
 
 // first element of the hoisted pre-activation row of token (t, row): direct, or through the per-word table
@@ -518,7 +519,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             int stage = 0; uint32_t phase = 0;
             const uint32_t box_bytes = (uint32_t)hr * 128u;
             for (int t = 1; t < p.T; ++t) {
-                const int need = p.ctas_per_group * 8 * t;   // 8 epilogue warps per half and CTA publish h_{t-1}
+                const int need = p.ctas_per_group * (p.pub_cta ? 1 : 8) * t;   // publishes of h_{t-1} per half: one per CTA, or one per epilogue warp
                 for (int hs_ = 0; hs_ < 2; ++hs_) {
                     int* counter = p.counters + 2 * g + hs_;
                     while (ld_acquire(counter) < need) { }
@@ -690,8 +691,13 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             // drain this warp's own h stores (made visible to it by the warp barrier)
             tc_fence_before();
             if (tracer) FSMG_TR(t, 6);
-            __syncwarp();
-            if (lane == 0) { if (tracer) FSMG_TR(t, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(t, 8); }
+            if (p.pub_cta) {     // barrier among the half's 8 warps, then one cumulative gpu-scope release
+                named_bar_sync(1 + hs_, 256);
+                if (us == 0 && quad == 0 && lane == 0) { if (tracer) FSMG_TR(t, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(t, 8); }
+            } else {
+                __syncwarp();
+                if (lane == 0) { if (tracer) FSMG_TR(t, 7); red_release_add(counter, 1); if (tracer) FSMG_TR(t, 8); }
+            }
             if (ok) {
                 __half* gout = p.gates + r * p.G4p + ucol;
                 float* cdst = p.c + r * p.H + ucol;
@@ -1501,6 +1507,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const int32_t
                 if (p.stages >= 2 || ks == 1) break;
             }
             p.ks = ks;
+            p.pub_cta = c.lstm_pub_cta;
             if (pl.U == 32) rc = lstm_launch(tc::lstm_fwd_split_kernel<32>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
             else rc = lstm_launch(tc::lstm_fwd_split_kernel<16>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
         } else {
