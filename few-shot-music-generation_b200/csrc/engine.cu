@@ -18,6 +18,7 @@
 #include "tc_gemm.cuh"
 #include "tc_lstm.cuh"
 #include "unigram.cuh"
+#include "probe.cuh"
 
 namespace fsmg {
 
@@ -1194,6 +1195,12 @@ int fsmg_debug_prep_tokens(fsmg_handle* h, const int32_t* d_tokens, int32_t n_se
                                                                           reinterpret_cast<int*>(h->scalars + 32));
     FSMG_LAUNCH_OK();
     return FSMG_OK;
+}
+
+// hardware probe: TMEM placement of D for tcgen05.mma.cta_group::2 with the given M, N (d_out: fp32 [2 CTAs][128 lanes][N])
+int fsmg_debug_mma_probe(int32_t m, int32_t n, float* d_out, void* stream) {
+    if (!d_out) return set_error(FSMG_ERR_INVALID, "null output");
+    return mma_probe_2sm(m, n, d_out, (cudaStream_t)stream);
 }
 
 int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const void* d_b_f16, float* d_c,

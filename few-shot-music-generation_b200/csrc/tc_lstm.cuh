@@ -1024,13 +1024,19 @@ constexpr int LSTM_BSPLIT_THREADS = 64 + 512;
 constexpr int LSTM_BSPLIT_MAX_STAGES = 16;
 constexpr int LSTM_BSPLIT_BAR_BYTES = 512;
 
-template <int U, int NSUB>
+// HALF_M (NSUB = 2 only, <= 64 rows per CTA and sub-group): the pair's MMA is 128 x 2U x 16 instead of 256 x 2U x 16 — each CTA feeds 64
+// rows of A instead of 128 (the sub-group only has 40 at configs[1]), which is what a small-N MMA costs.  Measured with
+// fsmg_debug_mma_probe: tcgen05.mma.cta_group::2 with M = 128 puts row r of CTA c's 64 rows in TMEM lane r for output columns
+// [0, N/2) and in lane 64 + r for columns [N/2, N), both at TMEM columns [0, N/2).  With N = 2U that is: lanes 0-63 = the rows x the
+// first CTA's unit slice, lanes 64-127 = the same rows x the second CTA's unit slice — every lane quadrant has rows to work on, the
+// accumulator takes U columns instead of 2U, and the columns saved hold c_{t-1} for a 2-way unit split of the epilogue.
+template <int U, int NSUB, bool HALF_M = false>
 __global__ void __launch_bounds__(LSTM_BSPLIT_THREADS, 1)
 lstm_bwd_pair2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_dg, LstmParams p) {
     constexpr int CHUNK_W = U * 128;
-    constexpr int UH = NSUB == 1 ? U / 2 : U;   // units per epilogue thread
-    constexpr int ACC_COLS = 2 * U;             // one sub-group: both unit slices of the pair
-    constexpr bool STAGE_CPREV = NSUB == 1;     // c_{t-1} staged in TMEM too (NSUB = 2 has no columns left: read from L2)
+    constexpr int UH = (NSUB == 1 || HALF_M) ? U / 2 : U;   // units per epilogue thread
+    constexpr int ACC_COLS = HALF_M ? U : 2 * U;            // one sub-group's accumulator (see the M = 128 layout above)
+    constexpr bool STAGE_CPREV = NSUB == 1 || HALF_M;       // c_{t-1} staged in TMEM too (else no columns left: read from L2)
     constexpr int STG_COLS = (STAGE_CPREV ? 4 : 3) * UH;   // per epilogue quartet: gates (2 UH words) | c (UH) [| c_prev (UH)]
     constexpr uint32_t TMEM_COLS = tmem_cols_pow2(NSUB * ACC_COLS + 4 * STG_COLS);
     static_assert(NSUB * ACC_COLS + 4 * STG_COLS <= 512, "TMEM budget");
@@ -1115,7 +1121,7 @@ lstm_bwd_pair2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             mbar_wait(w_bar, 0);
             mbar_arrive_remote_release(peer_w, 0);
         } else if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_m(256, 2 * U);
+            constexpr uint32_t idesc = make_idesc_m(HALF_M ? 128 : 256, 2 * U);
             mbar_wait(w_bar, 0);
             mbar_wait(peer_w, 0);
             tc_fence_after();
@@ -1154,22 +1160,26 @@ lstm_bwd_pair2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             }
         }
     } else {
-        // ===== epilogue: 16 warps x 32 lanes; thread <-> one row (TMEM lane), UH units.
-        //   NSUB = 1: quartet qd -> unit slice of the pair (qd & 1), unit half (qd >> 1)
-        //   NSUB = 2: quartet qd -> sub-group (qd >> 1), unit slice of the pair (qd & 1)
+        // ===== epilogue: 16 warps x 32 lanes; thread <-> one row, UH units.  quartet qd = (warp - 2) / 4, TMEM lane quadrant quad = warp % 4
+        //   NSUB = 1:          unit slice of the pair us = qd & 1, unit half qd >> 1,              row = quad * 32 + lane
+        //   NSUB = 2:          sub-group qd >> 1, unit slice us = qd & 1 (all U units),            row = quad * 32 + lane
+        //   NSUB = 2, HALF_M:  sub-group qd >> 1, unit half qd & 1, unit slice us = quad >> 1,     row = (quad & 1) * 32 + lane
+        //   NSUB = 1, HALF_M:  unit half qd & 1 (quartets 2, 3 idle), unit slice us = quad >> 1,   row = (quad & 1) * 32 + lane
         const int quad = warp & 3;
         const int qd = (warp - 2) >> 2;
         const int sub = NSUB == 1 ? 0 : qd >> 1;
-        const int us = qd & 1;
-        const int ucol = ((j & ~1) + us) * U + (NSUB == 1 ? (qd >> 1) * UH : 0);   // first hidden unit of this thread
+        const int us = HALF_M ? quad >> 1 : qd & 1;
+        const int uhalf = HALF_M ? qd & 1 : NSUB == 1 ? qd >> 1 : 0;
+        const int ucol = ((j & ~1) + us) * U + uhalf * UH;   // first hidden unit of this thread
         const int row_base = group_row0 + sub * 2 * hr + prank * hr;
         const int rows = max(0, min(hr, group_rows - sub * 2 * hr - prank * hr));
-        const int lrow = quad * 32 + lane;
-        const bool ok = lrow < rows;
-        const bool warp_active = quad * 32 < rows;          // warp-uniform: quadrants without rows only keep the barriers in step
+        const int lrow0 = HALF_M ? (quad & 1) * 32 : quad * 32;
+        const int lrow = lrow0 + lane;
+        const bool ok = lrow < rows && !(HALF_M && NSUB == 1 && qd >= 2);
+        const bool warp_active = lrow0 < rows && !(HALF_M && NSUB == 1 && qd >= 2);   // warp-uniform: warps without work only keep the barriers in step
         int* counter = p.counters + 2 * g + sub;
         const bool tracer = (qd == 0 && quad == 0 && lane == 0);
-        const uint32_t t_acc = tmem_base + (uint32_t)(sub * ACC_COLS + us * U + (NSUB == 1 ? (qd >> 1) * UH : 0)) + ((uint32_t)(quad * 32) << 16);
+        const uint32_t t_acc = tmem_base + (uint32_t)(sub * ACC_COLS + (HALF_M ? 0 : us * U) + uhalf * UH) + ((uint32_t)(quad * 32) << 16);
         const uint32_t t_stg = tmem_base + (uint32_t)(NSUB * ACC_COLS + qd * STG_COLS) + ((uint32_t)(quad * 32) << 16);
         float dc_state[UH];
 #pragma unroll
@@ -1319,10 +1329,10 @@ static inline void lstm_ring(int w_bytes, int box_rows, int mt, int* stage_bytes
 }
 
 // pair + split backward: 16-deep ring of the narrow sub-group boxes, barrier block of LSTM_BSPLIT_BAR_BYTES
-static inline void lstm_ring_bsplit(int w_bytes, int box_rows, int ks, int* box_pitch, int* stage_bytes, int* stages) {
+static inline void lstm_ring_bsplit(int w_bytes, int box_rows, int ks, int tile_rows, int* box_pitch, int* stage_bytes, int* stages) {
     const int avail = tc::LSTM_MAX_DYN - 1024 - tc::LSTM_BSPLIT_BAR_BYTES - w_bytes;
     const int pitch = (int)round_up((int64_t)box_rows * 128, 1024);
-    const int window = 128 * 128;       // the UMMA descriptors address a full 128-row tile from every box base
+    const int window = tile_rows * 128;   // the UMMA descriptors address a full tile (128 rows per CTA, 64 with HALF_M) from every box base
     const int sb = ks * pitch;
     int n = (avail - (window - pitch)) / sb;
     if (n > tc::LSTM_BSPLIT_MAX_STAGES) n = tc::LSTM_BSPLIT_MAX_STAGES;
@@ -1535,10 +1545,12 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
     const int nsub = mode == 2 ? 2 : 1;
     const int sub_rows = (int)round_up(cdiv(pl.rows_per_group, 2 * nsub), 8);
     int bs_stage = 0, bs_stages = 0, bs_pitch = 0;
-    int ks = c.lstm_ks > 0 ? c.lstm_ks : (sub_rows <= 32 ? 8 : 4);
+    int ks = c.lstm_ks > 0 ? c.lstm_ks : (sub_rows <= 64 ? 8 : 4);
     while (ks > 1 && ((4 * H / 64) % ks) != 0) ks >>= 1;
-    lstm_ring_bsplit((4 * H / 64) * pl.U * 128, sub_rows, ks, &bs_pitch, &bs_stage, &bs_stages);
-    while (bs_stages < 2 && ks > 1) { ks >>= 1; lstm_ring_bsplit((4 * H / 64) * pl.U * 128, sub_rows, ks, &bs_pitch, &bs_stage, &bs_stages); }
+    const bool half_m = sub_rows <= 64 && c.lstm_half_m;      // 128-row pair MMAs (64 rows of A per CTA)
+    const int tile_rows = half_m ? 64 : 128;
+    lstm_ring_bsplit((4 * H / 64) * pl.U * 128, sub_rows, ks, tile_rows, &bs_pitch, &bs_stage, &bs_stages);
+    while (bs_stages < 2 && ks > 1) { ks >>= 1; lstm_ring_bsplit((4 * H / 64) * pl.U * 128, sub_rows, ks, tile_rows, &bs_pitch, &bs_stage, &bs_stages); }
     const bool bsplit = mode != 0 && pl.pair && pl.rows_per_group >= 16 && bs_stages >= 2 && sub_rows <= 128;
     rc = make_map_f16_3d(c, &md, dgates, (uint64_t)4 * H, (uint64_t)N, (uint64_t)T, (uint64_t)G4p, (uint64_t)N * G4p, 64,
                          (uint32_t)(bsplit ? sub_rows : pl.box_rows));
@@ -1564,14 +1576,18 @@ static inline int tc_lstm_backward(TcContext& c, const float* dh_out, const __ha
             p.stages = bs_stages;
             p.ks = ks;
             p.box_pitch = bs_pitch;
-            if (pl.U == 32 && nsub == 1) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 1>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            if (half_m && pl.U == 32 && nsub == 2) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 2, true>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else if (half_m && nsub == 2) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<16, 2, true>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else if (half_m && pl.U == 32) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 1, true>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else if (half_m) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<16, 1, true>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
+            else if (pl.U == 32 && nsub == 1) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 1>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
             else if (pl.U == 32) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<32, 2>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
             else if (nsub == 1) rc = lstm_launch(tc::lstm_bwd_pair2_kernel<16, 1>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
             else rc = lstm_launch(tc::lstm_bwd_pair2_kernel<16, 2>, G * pl.C, tc::LSTM_BSPLIT_THREADS, 2, smem, mw, md, p, s);
         } else {
             FSMG_LSTM_DISPATCH(lstm_bwd_persistent_kernel, rc, true);
         }
-        if (trace && !rc) lstm_trace_dump(c, bsplit ? (nsub == 2 ? "lstm_bwd_pair2<NSUB=2>" : "lstm_bwd_pair2<NSUB=1>") : "lstm_bwd_persistent", s);
+        if (trace && !rc) lstm_trace_dump(c, bsplit ? (half_m ? (nsub == 2 ? "lstm_bwd_pair2<NSUB=2, M=128>" : "lstm_bwd_pair2<NSUB=1, M=128>") : nsub == 2 ? "lstm_bwd_pair2<NSUB=2>" : "lstm_bwd_pair2<NSUB=1>") : "lstm_bwd_persistent", s);
         if (rc) return rc;
     }
     return 0;

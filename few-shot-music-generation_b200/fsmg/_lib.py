@@ -64,6 +64,7 @@ SYMBOLS = {
     "fsmg_last_launch_count": (C.c_int64, [_P]),
     "fsmg_token_range_errors": (C.c_int, [_P, C.POINTER(C.c_int64), _P]),
     "fsmg_debug_prep_tokens": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
+    "fsmg_debug_mma_probe": (C.c_int, [C.c_int32, C.c_int32, _P, _P]),
     "fsmg_debug_gemm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fsmg_gather_token_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
     "fsmg_unigram_step": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),

@@ -177,6 +177,11 @@ int64_t fsmg_last_launch_count(const fsmg_handle* h);
 int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const void* d_b_f16,
                     float* d_c, int32_t a_mn_major, int32_t b_mn_major, int32_t use_simt, void* stream);
 
+/* Hardware probe (test infrastructure): where tcgen05.mma.cta_group::2 places the rows of D in each CTA's tensor memory for
+ * the given instruction shape.  D[r, n] = 256 r + n is computed by one CTA pair; d_out receives fp32 [2 CTAs][128 lanes][n]
+ * (-1 = cell not written by the instruction).  The recurrent kernels' epilogues rely on this layout. */
+int fsmg_debug_mma_probe(int32_t m, int32_t n, float* d_out, void* stream);
+
 /* One in-place softmax-gradient pass over an fp16 logits block [rows, ld] (K7/K8 of the hot path, reference
  * lstm_baseline.py:70-75 + tf.gradients through sequence_loss): logits[r, v] <- exp(logits[r, v] - lse[r]) - (v == y[r]),
  * db[v] += alpha * sum_r of that, for v < vocab1 (columns vocab1..ld-1 are zeroed).  mode/param/waves select the kernel
