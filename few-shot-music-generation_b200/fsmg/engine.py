@@ -97,7 +97,9 @@ class Engine:
         self._pinned_np = None
         self._checked_corpora = set()
         self._overlap = False
-        if self.world > 1 and os.environ.get("FSMG_AR_OVERLAP", "1") != "0":
+        # Off by default: measured on 2 and 8 B200 (profiles/r2_optimization_log.md) the overlapped schedule is within noise of the
+        # single all-reduce — the collective is ~0.3 ms of an 11 ms step and what N > 1 loses is mostly cross-GPU skew.
+        if self.world > 1 and os.environ.get("FSMG_AR_OVERLAP", "0") == "1":
             self._setup_overlapped_allreduce()
 
     # ---- data-parallel gradient all-reduce overlapped with the backward pass ----------------------------------------

@@ -10,7 +10,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_two_gpu_data_parallel_step_matches_single_process(built_lib):
+@pytest.mark.parametrize("overlap", ["0", "1"], ids=["single_allreduce", "stage_event_overlap"])
+def test_two_gpu_data_parallel_step_matches_single_process(built_lib, overlap):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
@@ -18,7 +19,7 @@ def test_two_gpu_data_parallel_step_matches_single_process(built_lib):
     worker = Path(__file__).with_name("dp_worker.py")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
                           "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300), str(worker)],
-                         capture_output=True, text=True, timeout=600)
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, FSMG_AR_OVERLAP=overlap))
     (Path(__file__).resolve().parents[1] / "gpurun_out").mkdir(exist_ok=True)
     (Path(__file__).resolve().parents[1] / "gpurun_out" / "dp_worker_last.log").write_text(out.stdout[-20000:] + "\n==== stderr ====\n" + out.stderr[-20000:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
