@@ -129,7 +129,7 @@ struct fsmg_handle {
     // caller-owned events recorded INSIDE forward_backward (fsmg_set_stage_events): [0] softmax_w / softmax_b gradients final (after the
     // projection backward), [1] embedding gradient final.  A data-parallel caller all-reduces those slices on a side stream while the
     // recurrent backward still runs.
-    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[3] = {nullptr, nullptr, nullptr};   // [2]: sum of the per-token NLL final (fsmg_set_loss_event)
     fsmg::TcContext tc;
 };
 
@@ -967,6 +967,7 @@ static int enqueue_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int
     if ((rc = record_stage_event(h, 0, s))) return rc;   // softmax_w / softmax_b gradients are final
     sum_f32_kernel<<<148, 256, 0, s>>>(d_nll ? d_nll : h->nll, (int64_t)n_seqs * h->T, h->grads + h->n_params);
     LAUNCH_COUNT(h);
+    if ((rc = record_stage_event(h, 2, s))) return rc;   // the step's loss (sum of NLL, token count) can be read back from here on
     rc = backward_lstm(h, n_seqs, loss_scale, s);
     if (rc) return rc;
     FSMG_LAUNCH_OK();
@@ -1027,6 +1028,14 @@ int fsmg_set_stage_events(fsmg_handle* h, void* ev_softmax_grads, void* ev_embed
     h->stage_ev[1] = (cudaEvent_t)ev_embedding_grads;
     h->tc.lstm_reserve_sms = reserve_sms;
     for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // captured graphs hold the old events / grid sizes
+    h->step_graphs.clear();
+    return FSMG_OK;
+}
+
+int fsmg_set_loss_event(fsmg_handle* h, void* ev_loss_ready) {
+    if (!h) return set_error(FSMG_ERR_INVALID, "null handle");
+    h->stage_ev[2] = (cudaEvent_t)ev_loss_ready;
+    for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // captured graphs hold the old event
     h->step_graphs.clear();
     return FSMG_OK;
 }

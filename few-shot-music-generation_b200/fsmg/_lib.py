@@ -52,6 +52,7 @@ SYMBOLS = {
     "fsmg_forward_nll": (C.c_int, [_P, _P, C.c_int32, _P, _P, _P]),
     "fsmg_forward_backward": (C.c_int, [_P, _P, C.c_int32, C.c_float, _P, _P]),
     "fsmg_set_stage_events": (C.c_int, [_P, _P, _P, C.c_int32]),
+    "fsmg_set_loss_event": (C.c_int, [_P, _P]),
     "fsmg_param_range": (C.c_int, [_P, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fsmg_apply_update": (C.c_int, [_P, C.c_int64, _P, _P]),
     "fsmg_sample_greedy": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),

@@ -37,6 +37,20 @@ def glorot_uniform_init(shapes: Dict[str, tuple], seed: int) -> Dict[str, np.nda
     return out
 
 
+class DeviceLoss:
+    """Mean loss of a step, still on the device: `sum_nll` is a 1-element view of the gradient buffer's scalar slot, valid until the
+    next step; float() reads it back (synchronising) and divides on the host — no extra kernel in the step."""
+    __slots__ = ("sum_nll", "tokens")
+
+    def __init__(self, sum_nll: torch.Tensor, tokens: float):
+        self.sum_nll, self.tokens = sum_nll, tokens
+
+    def __float__(self) -> float:
+        return float(self.sum_nll) / (self.tokens + 1e-12)
+
+    item = __float__
+
+
 class Engine:
     """One engine per process/GPU.  `config` uses the reference's keys (lstm_baseline.py:21-29)."""
 
@@ -97,6 +111,16 @@ class Engine:
         self._pinned_np = None
         self._checked_corpora = set()
         self._overlap = False
+        # single GPU: the loss of a step is final ~40 % into it.  It is read back from a side stream behind an event recorded inside
+        # the step graph, so train_host*() returns while the backward pass and the update still run and the caller's next episode is
+        # sampled / staged concurrently; later calls are stream-ordered behind the step.  FSMG_EARLY_LOSS=0: wait for the whole step.
+        self._early_loss = False
+        if self.world == 1 and os.environ.get("FSMG_EARLY_LOSS", "1") != "0":
+            self._loss_stream = torch.cuda.Stream(device=self.device)
+            self._ev_loss = torch.cuda.Event()
+            self._ev_loss.record(torch.cuda.current_stream(self.device))      # materialises the cudaEvent_t
+            _lib.check(self.lib.fsmg_set_loss_event(self.h, self._ev_loss.cuda_event))
+            self._early_loss = True
         # Off by default: measured on 2 and 8 B200 (profiles/r2_optimization_log.md) the overlapped schedule is within noise of the
         # single all-reduce — the collective is ~0.3 ms of an 11 ms step and what N > 1 loses is mostly cross-GPU skew.
         if self.world > 1 and os.environ.get("FSMG_AR_OVERLAP", "0") == "1":
@@ -212,11 +236,11 @@ class Engine:
         loss_scale = float(1.0 / (float(gt) + 1e-12))
         _lib.check(self.lib.fsmg_forward_backward(self.h, tokens.data_ptr(), n, loss_scale, 0, self._stream()))
 
-    def train_step_device(self, tokens: torch.Tensor, global_tokens: Optional[int] = None) -> torch.Tensor:
+    def train_step_device(self, tokens: torch.Tensor, global_tokens: Optional[int] = None) -> DeviceLoss:
         """One optimizer step on device-resident tokens.  Data parallel: every rank passes its
         shard; ONE all-reduce (sum) of the flat gradient buffer — which also carries sum(nll)
         and the per-occurrence embedding-gradient square norm — then clip+Adam on every rank.
-        Returns a 1-element device tensor holding the mean loss of the global batch."""
+        Returns the mean loss of the global batch as a DeviceLoss (read back with float())."""
         n = int(tokens.shape[0])
         gt = global_tokens if global_tokens is not None else n * self.T * self.world
         self.forward_backward(tokens, gt)
@@ -226,14 +250,20 @@ class Engine:
         self.global_step += 1
         self._last_gt = float(gt)
         self._last_gt_assumed = global_tokens is None
-        return self.grads[self.n_params: self.n_params + 1] / (float(gt) + 1e-12)
+        return DeviceLoss(self.grads[self.n_params: self.n_params + 1], float(gt))
 
     def _read_loss(self) -> float:
         """D2H of the step's scalars (sum of NLL, token count) after train_step_device: the mean loss of the global batch.  The
         all-reduced token count (grads[n_params + 2], written by the library) must equal the count the loss scale assumed —
         unequal shards across ranks would otherwise train with a silently wrong gradient scale."""
-        self._pinned_scal[:4].copy_(self.grads[self.n_params: self.n_params + 4], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+        if self._early_loss:
+            self._loss_stream.wait_event(self._ev_loss)
+            with torch.cuda.stream(self._loss_stream):
+                self._pinned_scal[:4].copy_(self.grads[self.n_params: self.n_params + 4], non_blocking=True)
+            self._loss_stream.synchronize()
+        else:
+            self._pinned_scal[:4].copy_(self.grads[self.n_params: self.n_params + 4], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
         total, count = float(self._pinned_scal[0]), float(self._pinned_scal[2])
         if self._last_gt_assumed and abs(count - self._last_gt) > 1e-6 * self._last_gt:
             raise FsmgError(f"ranks processed {count:.0f} tokens in this step but the loss was scaled for {self._last_gt:.0f}: "

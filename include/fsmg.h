@@ -132,6 +132,13 @@ int fsmg_forward_backward(fsmg_handle* h, const int32_t* d_tokens, int32_t n_seq
  * fsmg_param_range: [begin, end) element ranges of the flat buffers: 0 = embedding, 1 = LSTM kernels + biases,
  * 2 = softmax_w + softmax_b, 3 = the FSMG_GRAD_EXTRA scalars (gradient buffer only). */
 int fsmg_set_stage_events(fsmg_handle* h, void* ev_softmax_grads, void* ev_embedding_grads, int32_t reserve_sms);
+/* Same mechanism for the loss: ev_loss_ready (a caller-owned cudaEvent_t, NULL to disable) is recorded inside
+ * fsmg_forward_backward as soon as d_grads[param_count + 0] (sum of the per-token NLL) and [+ 2] (token count) are final —
+ * after the forward pass and the projection, before the recurrent backward.  A single-GPU caller reads the step's loss back
+ * from a side stream behind this event and returns it to the training loop (sess.run's fetched avg_neg_log,
+ * lstm_baseline.py:104-105) while the backward pass and the update still run; every later call is ordered behind them on
+ * `stream`. */
+int fsmg_set_loss_event(fsmg_handle* h, void* ev_loss_ready);
 int fsmg_param_range(const fsmg_handle* h, int32_t which, int64_t* begin, int64_t* end);
 
 /* clip_by_global_norm + Adam + exponential_decay + global_step++ (lstm_baseline.py:77-87) on the
