@@ -2,8 +2,10 @@
 //
 // One persistent, warp-specialised GEMM core (fp16 x fp16 -> fp32 in TMEM) with pluggable epilogues:
 //   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B, mbarrier complete_tx)
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, cta_group::1)
-//   warps 2..5  : epilogue (tcgen05.ld 32x32b, one accumulator row per thread), double-buffered TMEM
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (default CL = 2: the leader CTA of a cluster of two issues ONE
+//                 tcgen05.mma.cta_group::2 of 256 x BN x 16 for the pair; CL = 1: UMMA 128 x BN x 16, cta_group::1)
+//   warps 2..17 : sixteen epilogue warps (TMEM lane quadrant x column quarter, tcgen05.ld 32x32b in 16-column chunks),
+//                 double-buffered TMEM accumulators (single-buffered for the 256 x 512 pair tiles)
 // C[M,N] (op)= alpha * A * B^T with A, B each either K-major (row = m/n, contiguous k) or MN-major
 // (row = k, contiguous m/n) — the latter serves the weight-gradient contractions over tokens.
 //

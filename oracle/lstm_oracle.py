@@ -6,13 +6,16 @@ together with the TensorFlow-1.x library semantics it relies on (SURVEY.md Appen
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
 import this module; the product path (``fsmg`` + ``libfsmg.so``) never does.
 
-PARITY UNPINNED: the reference's arithmetic lives in TensorFlow 1.x (version unpinned,
-absent from ``requirements.txt``; not installable here), and its only test
-(``src/train/test_seed.py:45-65``) needs the real datasets and TF's initialiser RNG
-stream.  No golden vector of the reference can therefore be evaluated in this
-container.  The oracle is pinned instead against an independent formulation
-(``oracle/torch_ref.py``: ``torch.nn.LSTM`` + autograd) and against committed fixtures
-generated by ``tests/golden/make_golden.py``.
+PARITY PARTLY PINNED.  Pinned to the reference itself (bit-exact, ``tests/test_reference_pin.py``
+running the unmodified reference code + the committed outputs ``tests/golden/reference_*``): the
+input/target shift of ``shift_inputs`` / ``episode_train_tokens`` (reference
+``models/base_model.py:57-86``) that every NLL comparison feeds.  UNPINNED: the graph arithmetic
+itself — it lives in TensorFlow 1.x (version unpinned, absent from ``requirements.txt``; not
+installable here), and the reference's only numeric test (``src/train/test_seed.py:45-65``) needs
+the real datasets and TF's initialiser RNG stream, so no golden value of it can be evaluated in
+this container.  For that part the oracle is anchored on an independent formulation
+(``oracle/torch_ref.py``: ``torch.nn.LSTM`` + autograd), finite differences and the committed
+fixtures of ``tests/golden/make_golden.py``.
 
 Every function cites the reference lines it follows.  ``dtype`` selects the arithmetic
 (float64 = ground truth, float32 = "the reference's CPU path").
