@@ -112,6 +112,8 @@ struct fsmg_handle {
     __half* dlogits_b[2] = {nullptr, nullptr};
     cudaStream_t aux[2] = {nullptr, nullptr};
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_dh[2] = {nullptr, nullptr}, ev_dws[2] = {nullptr, nullptr};
+    cudaEvent_t ev_sort_fork = nullptr, ev_sort_join = nullptr;   // token sort of the layer-0 segment sums runs beside the forward pass
+    bool sort_forked = false;
     int overlap = 1;
     int dws_transposed = 1;  // softmax_w gradient accumulated as [V', H] (FSMG_DWS_T=0: [H, V'])
     int strip_overlap = 0;   // background softmax-gradient pass beside the dH / dWs GEMMs (FSMG_STRIP_OVERLAP=1; measured slower)
@@ -333,6 +335,24 @@ static bool layer0_word_backward(fsmg_handle* h, int N) {
            (int64_t)h->V1 < (int64_t)N * h->T && h->Ep == h->E;
 }
 
+// counting sort of the token rows by input word (layer-0 segment sums, see backward_lstm): depends on the tokens only
+static int token_sort(fsmg_handle* h, int N, cudaStream_t s) {
+    const int TB = 256, V1 = h->V1;
+    const int64_t NT = (int64_t)N * h->T;
+    int32_t* counts = h->tok_counts;
+    int32_t* offsets = counts + (V1 + 8);
+    int32_t* cursor = offsets + (V1 + 8);
+    FSMG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(V1 + 8), s));
+    token_hist_kernel<<<cdiv(NT, TB), TB, 0, s>>>(h->x_ids, NT, counts);
+    token_scan_kernel<<<1, 1024, 0, s>>>(counts, V1, offsets, cursor);
+    token_fill_kernel<<<cdiv(NT, TB), TB, 0, s>>>(h->x_ids, NT, cursor, h->sorted_rows, h->sorted_tok);
+    h->launches += 3;
+    FSMG_LAUNCH_OK();
+    return FSMG_OK;
+}
+
+static bool layer0_word_backward(fsmg_handle* h, int N);
+
 static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, bool train, cudaStream_t s) {
     const int T = h->T, H = h->H, TB = 256;
     const int64_t NT = (int64_t)N * T;
@@ -349,6 +369,17 @@ static int forward_lstm(fsmg_handle* h, const int32_t* d_tokens, int N, bool tra
         }
     }
     FSMG_LAUNCH_OK();
+    // the token sort the backward pass needs depends on x_ids only: fork it onto an auxiliary stream here (also inside a graph
+    // capture: a cross-stream fork/join) so that its three small kernels run beside the forward pass instead of after the recurrent backward
+    h->sort_forked = false;
+    if (train && !h->prof.on && h->aux[0] != nullptr && layer0_word_backward(h, N)) {
+        FSMG_CUDA_OK(cudaEventRecord(h->ev_sort_fork, s));
+        FSMG_CUDA_OK(cudaStreamWaitEvent(h->aux[0], h->ev_sort_fork, 0));
+        int rc0 = token_sort(h, N, h->aux[0]);
+        if (rc0) return rc0;
+        FSMG_CUDA_OK(cudaEventRecord(h->ev_sort_join, h->aux[0]));
+        h->sort_forked = true;
+    }
     for (int li = 0; li < h->L; ++li) {
         LayerBuf& l = h->layers[li];
         const __half* in = li == 0 ? h->xemb : h->layers[li - 1].hs;
@@ -591,13 +622,10 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
         if (seg) {
             ProfScope ps_seg(h, PH_WGRAD, s);
             const int V1 = h->V1;
-            int32_t* counts = h->tok_counts;
-            int32_t* offsets = counts + (V1 + 8);
-            int32_t* cursor = offsets + (V1 + 8);
-            FSMG_CUDA_OK(cudaMemsetAsync(counts, 0, sizeof(int32_t) * (size_t)(V1 + 8), s));
-            token_hist_kernel<<<cdiv(NT, TB), TB, 0, s>>>(h->x_ids, NT, counts);
-            token_scan_kernel<<<1, 1024, 0, s>>>(counts, V1, offsets, cursor);
-            token_fill_kernel<<<cdiv(NT, TB), TB, 0, s>>>(h->x_ids, NT, cursor, h->sorted_rows, h->sorted_tok);
+            if (h->sort_forked) {                 // sorted beside the forward pass: join
+                FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_sort_join, 0));
+                h->sort_forked = false;
+            } else if ((rc = token_sort(h, N, s))) return rc;
             FSMG_CUDA_OK(cudaMemsetAsync(h->seg32, 0, sizeof(float) * (size_t)V1 * h->G4, s));
             constexpr int RPB = 64;
             segsum_rows_kernel<RPB><<<dim3(cdiv(h->G4, 1024), cdiv(NT, RPB)), 128, 0, s>>>(h->dgates, h->G4p, h->G4, h->sorted_tok, h->sorted_rows, NT,
@@ -605,7 +633,7 @@ static int backward_lstm(fsmg_handle* h, int N, float loss_scale, cudaStream_t s
             // fp16 operand copy of S + db = loss_scale * colsum(S)  (= colsum(dgates))
             seg_finish_kernel<64><<<dim3(cdiv(h->G4p, 1024), cdiv(V1, 64)), 128, 0, s>>>(h->seg32, h->G4, V1, h->G4, h->seg16, h->G4p, loss_scale,
                                                                                         h->grads + l.b_off);
-            h->launches += 5;
+            h->launches += 2;
             FSMG_LAUNCH_OK();
             float* gK0 = h->grads + l.k_off;
             // dEmbedding = loss_scale * S * K[:E]^T   (dense [V', E]; rows of words absent from the batch come out zero).  First of the three
@@ -869,6 +897,8 @@ void fsmg_destroy(fsmg_handle* h) {
         if (h->ev_dh[i]) cudaEventDestroy(h->ev_dh[i]);
         if (h->ev_dws[i]) cudaEventDestroy(h->ev_dws[i]);
     }
+    if (h->ev_sort_fork) cudaEventDestroy(h->ev_sort_fork);
+    if (h->ev_sort_join) cudaEventDestroy(h->ev_sort_join);
     delete h;
 }
 
@@ -923,6 +953,8 @@ int fsmg_bind(fsmg_handle* h, float* d_params, float* d_grads, float* d_adam_m, 
             FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dh[i], cudaEventDisableTiming));
             FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dws[i], cudaEventDisableTiming));
         }
+        FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_sort_fork, cudaEventDisableTiming));
+        FSMG_CUDA_OK(cudaEventCreateWithFlags(&h->ev_sort_join, cudaEventDisableTiming));
     }
     for (auto& e : h->step_graphs) if (e.exec) cudaGraphExecDestroy(e.exec);   // graphs hold the old buffer addresses
     h->step_graphs.clear();
