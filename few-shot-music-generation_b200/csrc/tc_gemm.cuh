@@ -1071,6 +1071,7 @@ struct TcContext {
     int lstm_bsplit = -1;      // backward recurrent kernel (FSMG_LSTM_BSPLIT): -1 auto, 0 first-generation pair kernel, 1 lstm_bwd_pair2<NSUB=1>, 2 <NSUB=2>
     int lstm_ks = 0;           // backward pair2 kernel: K chunks per ring stage (FSMG_LSTM_KS = 1, 2, 4, 8; 0 = auto)
     int lstm_half_m = 1;       // backward pair2 NSUB = 2: 128-row pair MMAs when a sub-group has <= 64 rows per CTA (FSMG_LSTM_HALF_M=0: 256-row)
+    int lstm_nh = 0;           // forward split kernel: halves in use (FSMG_LSTM_NH = 1, 2; 0 = auto: 1 up to 32 rows per group)
     int lstm_pub_cta = 0;      // forward split kernel: one release per (CTA, half) instead of per warp (FSMG_LSTM_PUB_CTA=1)
     int lstm_fks = 4;          // forward split kernel: K chunks per ring stage (FSMG_LSTM_FKS = 1, 2, 4)
     int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
@@ -1110,6 +1111,8 @@ static inline int tc_init(TcContext& c) {
     if (envks && atoi(envks) > 0) c.lstm_ks = atoi(envks);
     const char* envhm = getenv("FSMG_LSTM_HALF_M");
     if (envhm) c.lstm_half_m = atoi(envhm);
+    const char* envnh = getenv("FSMG_LSTM_NH");
+    if (envnh) c.lstm_nh = atoi(envnh);
     const char* envpc = getenv("FSMG_LSTM_PUB_CTA");
     if (envpc) c.lstm_pub_cta = atoi(envpc);
     const char* envfks = getenv("FSMG_LSTM_FKS");

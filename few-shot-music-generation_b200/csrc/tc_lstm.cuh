@@ -149,6 +149,7 @@ struct LstmParams {
     int ks;                // pair + split backward: 64-column K chunks (TMA boxes) per ring stage = per full/empty barrier round trip
     int box_pitch;         // bytes between the boxes of one stage (box rows x 128 B rounded to the 1024-B swizzle atom)
     int pub_cta;           // forward split kernel: one release per (CTA, half) behind a named barrier instead of one per warp
+    int nh;                // forward split kernel: halves in use (2; 1 for groups of a few rows, where a second half only doubles the MMA count)
 };
 
 // first element of the hoisted pre-activation row of token (t, row): direct, or through the per-word table
@@ -520,7 +521,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             const uint32_t box_bytes = (uint32_t)hr * 128u;
             for (int t = 1; t < p.T; ++t) {
                 const int need = p.ctas_per_group * (p.pub_cta ? 1 : 8) * t;   // publishes of h_{t-1} per half: one per CTA, or one per epilogue warp
-                for (int hs_ = 0; hs_ < 2; ++hs_) {
+                for (int hs_ = 0; hs_ < p.nh; ++hs_) {
                     int* counter = p.counters + 2 * g + hs_;
                     while (ld_acquire(counter) < need) { }
                     if (hs_ == 0) FSMG_TR(t, 0);
@@ -552,7 +553,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             const uint64_t b_desc0 = make_smem_desc(smem_u32(sW), 16, 1024);
             const uint64_t a_step = (uint64_t)(p.box_pitch >> 4);
             for (int t = 1; t < p.T; ++t) {
-                for (int hs_ = 0; hs_ < 2; ++hs_) {
+                for (int hs_ = 0; hs_ < p.nh; ++hs_) {
                     const int b = hs_ * 2 + (t & 1);
                     mbar_wait(&pre_ready[b], pr_phase[b]);     // pre[t] of this half is staged in its buffer: every MMA accumulates
                     pr_phase[b] ^= 1;
@@ -587,6 +588,7 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
         const int quad = warp & 3;
         const int idx = (warp - 2) >> 2;
         const int hs_ = idx >> 1, us = idx & 1;
+        const int t_end = hs_ < p.nh ? p.T : 0;               // warps of an unused half have nothing to do (no barrier waits on them)
         const int row_base = group_row0 + hs_ * hr;
         const int rows = max(0, min(hr, group_rows - hs_ * hr));
         const int lrow = quad * 32 + lane;
@@ -619,8 +621,8 @@ lstm_fwd_split_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_co
             }
             tmem_st_wait();
         };
-        stage_pre(0);
-        for (int t = 0; t < p.T; ++t) {
+        if (t_end > 0) stage_pre(0);
+        for (int t = 0; t < t_end; ++t) {
             if (t + 1 < p.T) {
                 stage_pre(t + 1);
                 tc_fence_before();
@@ -1483,7 +1485,10 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const int32_t
     if (rc) return rc;
     // split schedule (default): two independently progressing halves per group hide each other's exchange latency
     const bool split = c.lstm_split && !pl.pair && pl.cls == 1 && pl.rows_per_group >= 16;
-    const int half_rows = (int)round_up(cdiv(pl.rows_per_group, 2), 8);
+    // groups of a few rows (configs[2]: 24) run ONE "half": a second one would only double the number of 128-row MMAs per step, which is
+    // what bounds the kernel there (measured: FSMG_LSTM_NH)
+    const int nh = c.lstm_nh > 0 ? c.lstm_nh : (pl.rows_per_group > 32 ? 2 : 1);
+    const int half_rows = nh == 2 ? (int)round_up(cdiv(pl.rows_per_group, 2), 8) : (int)round_up(pl.rows_per_group, 8);
     CUtensorMap mh_split = mh;
     if (split) {
         rc = make_map_f16_3d(c, &mh_split, hs, (uint64_t)H, (uint64_t)N, (uint64_t)T, (uint64_t)Hp, (uint64_t)N * Hp, 64, (uint32_t)half_rows);
@@ -1518,6 +1523,7 @@ static inline int tc_lstm_forward(TcContext& c, const __half* pre, const int32_t
             }
             p.ks = ks;
             p.pub_cta = c.lstm_pub_cta;
+            p.nh = nh;
             if (pl.U == 32) rc = lstm_launch(tc::lstm_fwd_split_kernel<32>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
             else rc = lstm_launch(tc::lstm_fwd_split_kernel<16>, G * pl.C, tc::LSTM_SPLIT_THREADS, 1, smem, mw, mh_split, p, s);
         } else {
