@@ -299,3 +299,53 @@ def test_saver_keeps_ten_checkpoints_and_restores_optimistically(torch_cuda, tmp
     for k, v in a.get_params().items():
         np.testing.assert_array_equal(v, before[k])
     assert a.global_step == 13
+
+
+def test_in_graph_events_do_not_change_the_step_and_fire_in_order(torch_cuda):
+    """fsmg_set_stage_events / fsmg_set_loss_event: caller-owned events recorded inside forward_backward (plain launches on the
+    first call, external event-record nodes of the captured graph afterwards).  The step's results must be bit-identical with
+    and without them, the loss read back behind the loss event must be the final one, and the parameter ranges must tile the
+    flat buffer in TF get_vars() order."""
+    torch = torch_cuda
+    from fsmg import _lib
+    from fsmg.engine import Engine
+    cfg = dict(name="lstm_baseline", input_size=500, embedding_size=64, hidden_size=64, n_layers=1, max_len=16, lr=5e-3, n_decay=10000,
+               max_grad_norm=5)
+    params = O.glorot_init(cfg, 3)
+    tok = O.synthetic_tokens(np.random.RandomState(2), (45, 16), 500, "zipf")
+    os.environ["FSMG_EARLY_LOSS"] = "0"
+    try:
+        plain = Engine(cfg, max_seqs=45, device="cuda:0")
+    finally:
+        os.environ.pop("FSMG_EARLY_LOSS", None)
+    evented = Engine(cfg, max_seqs=45, device="cuda:0")          # default: loss event set
+    assert evented._early_loss and not plain._early_loss
+    ev_soft, ev_emb = torch.cuda.Event(), torch.cuda.Event()
+    for ev in (ev_soft, ev_emb):
+        ev.record()
+    _lib.check(evented.lib.fsmg_set_stage_events(evented.h, ev_soft.cuda_event, ev_emb.cuda_event, 4))
+    plain.load_params(params)
+    evented.load_params(params)
+    state = O.TrainState(params, cfg, np.float64)
+    for step in range(5):                                          # call 1: plain launches, call 2: capture, then graph replays
+        want = O.train_step(state, tok)
+        a, b = plain.train_host(tok), evented.train_host(tok)
+        assert a == b and abs(a - want) < 1e-3 * want
+        # the softmax / embedding slices are final when their events have fired, and they fire before the step ends
+        ev_soft.synchronize()
+        ev_emb.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(plain.params, evented.params) and torch.equal(plain.adam_v, evented.adam_v)
+    ranges = []
+    for which in range(4):
+        b, e = C.c_int64(), C.c_int64()
+        _lib.check(evented.lib.fsmg_param_range(evented.h, which, C.byref(b), C.byref(e)))
+        ranges.append((b.value, e.value))
+    assert ranges[0][0] == 0 and ranges[0][1] == ranges[1][0] and ranges[1][1] == ranges[2][0] and ranges[2][1] == ranges[3][0]
+    assert ranges[3] == (evented.n_params, evented.n_params + 8)
+    names = [i["name"].rsplit("/", 1)[-1] for i in evented.infos]
+    assert names == ["embedding", "kernel", "bias", "softmax_w", "softmax_b"]
+    offs = [i["offset"] for i in evented.infos]
+    assert offs[0] == ranges[0][0] and offs[1] == ranges[1][0] and offs[3] == ranges[2][0]
+    plain.close()
+    evented.close()
