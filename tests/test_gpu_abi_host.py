@@ -335,7 +335,11 @@ def test_in_graph_events_do_not_change_the_step_and_fire_in_order(torch_cuda):
         ev_soft.synchronize()
         ev_emb.synchronize()
     torch.cuda.synchronize()
-    assert float((plain.params - evented.params).abs().max()) < 1e-4     # five Adam steps of ~5e-3 each: same up to RED order
+    init = Engine(cfg, max_seqs=1, device="cuda:0")
+    init.load_params(params)
+    update = float((plain.params - init.params).norm())
+    assert float((plain.params - evented.params).norm()) < 1e-3 * update      # same five Adam steps up to the order of the gradient REDs
+    init.close()
     ranges = []
     for which in range(4):
         b, e = C.c_int64(), C.c_int64()
