@@ -34,6 +34,7 @@ CASES = [
     (45, 5, 128, 128, 2),           # two layers
     (300, 4, 96, 512, 1),           # H=512: 16 CTAs/group, 128 KB resident slice, MT=1
     (1440, 3, 64, 512, 1),          # BASELINE configs[1] batch: 9 groups x 160 rows, MT=2
+    (1000, 3, 64, 512, 1),          # ragged: 8 full groups of 112 rows + one of 104, sub-groups of 32 / 24 rows per CTA
     (2400, 3, 64, 512, 1),          # larger than one launch can hold: batch slicing
     (45, 4, 64, 1024, 1),           # H=1024: U=16, 64 CTAs per group
     (300, 4, 64, 128, 2),           # N*T > V': layer 0 per word (pre-activation table + segment-sum gradients) under a second layer
