@@ -741,7 +741,8 @@ static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
     const float a = 1.0f / 2048.0f;
     int rc;
     for (int l = 0; l < h->L; ++l) {
-        rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l], 3 * h->Hp, h->KhT3[l], 3 * h->Hp, h->s_g, h->G4, a), false, false, s);
+        // accumulating GEMMs into buffers their consumers (cell / argmax kernels) leave zeroed: no memset node per token
+        rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l], 3 * h->Hp, h->KhT3[l], 3 * h->Hp, h->s_g, h->G4, a, nullptr, 0, 0, 1), false, false, s);
         if (rc) return rc;
         if (l > 0) {
             rc = gemm_f16(h, mk(n, h->G4, 3 * h->Hp, h->h3[l - 1], 3 * h->Hp, h->KxT3[l], 3 * h->Hp, h->s_g, h->G4, a, nullptr, 0, 0, 1), false, false, s);
@@ -758,7 +759,7 @@ static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
         LAUNCH_COUNT(h);
     }
     rc = gemm_f16(h, mk(n, h->V1, 3 * h->Hp, h->h3[h->L - 1], 3 * h->Hp, h->WsT3, 3 * h->Hp, h->s_logits2, h->Vp, a,
-                        h->params + h->sb_off), false, false, s);
+                        h->params + h->sb_off, 0, 0, 1), false, false, s);
     if (rc) return rc;
     argmax_rows_step_kernel<<<n, 256, 0, s>>>(h->s_logits2, h->Vp, h->V1, h->samp_ids, h->samp_out, 4096, h->s_step);
     h->launches += 1;
@@ -774,6 +775,8 @@ static int sample_greedy_split(fsmg_handle* h, int n, int n_tokens, int32_t* d_o
     fill_i32_kernel<<<cdiv(n, TB), TB, 0, s>>>(h->samp_ids, n, h->V);   // word = start word (lstm_baseline.py:138)
     LAUNCH_COUNT(h);
     FSMG_CUDA_OK(cudaMemsetAsync(h->s_step, 0, 2 * sizeof(int), s));
+    FSMG_CUDA_OK(cudaMemsetAsync(h->s_g, 0, sizeof(float) * (size_t)n * h->G4, s));          // accumulation targets of the decode-step GEMMs:
+    FSMG_CUDA_OK(cudaMemsetAsync(h->s_logits2, 0, sizeof(float) * (size_t)n * h->Vp, s));     // zeroed once, then kept zero by their consumers
     for (int l = 0; l < h->L; ++l) {   // zero_state (lstm_baseline.py:140)
         FSMG_CUDA_OK(cudaMemsetAsync(h->s_c[l], 0, sizeof(float) * n * H, s));
         FSMG_CUDA_OK(cudaMemsetAsync(h->h3[l], 0, sizeof(__half) * (size_t)n * 3 * h->Hp, s));

@@ -707,7 +707,7 @@ __global__ void split_weight_t_kernel(const float* __restrict__ in, int64_t ldi,
 // Sampler cell step: gates = G[n,:] (+ P[word[n],:] when P != null: the embedding row already multiplied by Wx, bias
 // included) -> c (in place, fp32) -> h -> split [hi | lo] for the next contractions.
 // scalar variant (one unit per thread) for hidden sizes that are not a multiple of 4
-__global__ void sample_cell_scalar_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ P, int64_t ldp,
+__global__ void sample_cell_scalar_kernel(float* __restrict__ G, int64_t ldg, const float* __restrict__ P, int64_t ldp,
                                           const int32_t* __restrict__ words, const float* __restrict__ bias,
                                           float* __restrict__ c_state, __half* __restrict__ h_split, int Hp, int n, int H) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -732,7 +732,7 @@ __global__ void sample_cell_scalar_kernel(const float* __restrict__ G, int64_t l
     o[Hp + u] = hi;
     o[2 * Hp + u] = lo;
 }
-__global__ void sample_cell_kernel(const float* __restrict__ G, int64_t ldg, const float* __restrict__ P, int64_t ldp,
+__global__ void sample_cell_kernel(float* __restrict__ G, int64_t ldg, const float* __restrict__ P, int64_t ldp,
                                    const int32_t* __restrict__ words, const float* __restrict__ bias,
                                    float* __restrict__ c_state, __half* __restrict__ h_split, int Hp, int n, int H) {
     // four consecutive units per thread (16-byte loads of the four gate blocks, the per-word table row and the cell state; 8-byte stores of
@@ -741,9 +741,14 @@ __global__ void sample_cell_kernel(const float* __restrict__ G, int64_t ldg, con
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * H4) return;
     const int r = (int)(idx / H4), u = (int)(idx % H4) * 4;
-    const float* g = G + (int64_t)r * ldg + u;
+    float* g = G + (int64_t)r * ldg + u;
     float4 gi = *reinterpret_cast<const float4*>(g), gj = *reinterpret_cast<const float4*>(g + H);
     float4 gf = *reinterpret_cast<const float4*>(g + 2 * H), go = *reinterpret_cast<const float4*>(g + 3 * H);
+    {   // consumed: left zeroed for the next step's accumulating (stream-K, RED) GEMM — no memset node per token
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(g) = z; *reinterpret_cast<float4*>(g + H) = z;
+        *reinterpret_cast<float4*>(g + 2 * H) = z; *reinterpret_cast<float4*>(g + 3 * H) = z;
+    }
     const float* add = P ? P + (int64_t)words[r] * ldp + u : bias ? bias + u : nullptr;
     float4 c4 = *reinterpret_cast<const float4*>(c_state + (int64_t)r * H + u);
     if (add) {
@@ -779,12 +784,12 @@ __global__ void sample_cell_kernel(const float* __restrict__ G, int64_t ldg, con
 // advances the counter (no separate bump kernel).  step_counter[0] = current step, step_counter[1] = arrival ticket of this launch.
 // (Zeroing the consumed logits / gate rows here and in the cell kernel, instead of the memset in front of each split-K GEMM, was
 // measured 3-5x slower per kernel: 12 -> 60 us and 6 -> 17 us under ncu, 49 -> 69 us per token.)
-__global__ void __launch_bounds__(256) argmax_rows_step_kernel(const float* __restrict__ logits, int64_t ld, int cols, int32_t* __restrict__ next_ids,
+__global__ void __launch_bounds__(256) argmax_rows_step_kernel(float* __restrict__ logits, int64_t ld, int cols, int32_t* __restrict__ next_ids,
                                                                int32_t* __restrict__ out, int64_t out_stride, int* __restrict__ step_counter) {
     __shared__ float sv[32];
     __shared__ int si[32];
     int r = blockIdx.x;
-    const float* row = logits + (int64_t)r * ld;
+    float* row = logits + (int64_t)r * ld;       // consumed rows are left zeroed for the next step's accumulating GEMM
     float best = -INFINITY;
     int bi = 0x7fffffff;
     auto take = [&](float v, int c) { if (v > best || (v == best && c < bi)) { best = v; bi = c; } };
@@ -801,11 +806,16 @@ __global__ void __launch_bounds__(256) argmax_rows_step_kernel(const float* __re
         }
 #pragma unroll
         for (int i = 0; i < VEC_ITERS; ++i) {
+            const int c = c0 + i * blockDim.x;
+            if (c < cols4) reinterpret_cast<float4*>(row)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC_ITERS; ++i) {
             const int c = 4 * (c0 + i * blockDim.x);
             take(v[i].x, c); take(v[i].y, c + 1); take(v[i].z, c + 2); take(v[i].w, c + 3);
         }
     }
-    for (int c = cols4 * 4 + threadIdx.x; c < cols; c += blockDim.x) take(row[c], c);
+    for (int c = cols4 * 4 + threadIdx.x; c < cols; c += blockDim.x) { take(row[c], c); row[c] = 0.0f; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         float ov = __shfl_xor_sync(0xffffffffu, best, o);
