@@ -713,8 +713,9 @@ __global__ void sample_cell_scalar_kernel(float* __restrict__ G, int64_t ldg, co
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * H) return;
     int r = (int)(idx / H), u = (int)(idx % H);
-    const float* g = G + (int64_t)r * ldg;
+    float* g = G + (int64_t)r * ldg;
     float gi = g[u], gj = g[H + u], gf = g[2 * H + u], go = g[3 * H + u];
+    g[u] = 0.0f; g[H + u] = 0.0f; g[2 * H + u] = 0.0f; g[3 * H + u] = 0.0f;   // consumed: left zeroed for the next step's accumulating GEMM
     if (P) {
         const float* p = P + (int64_t)words[r] * ldp;
         gi += p[u]; gj += p[H + u]; gf += p[2 * H + u]; go += p[3 * H + u];

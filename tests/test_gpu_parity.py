@@ -164,6 +164,25 @@ def test_sampling_long_sequence_matches_fp32_oracle(torch_cuda, flags):
     assert_greedy(params, got, O.sample_greedy(params, 96, np.float64))
 
 
+@pytest.mark.parametrize("flags", SAMPLERS)
+@pytest.mark.parametrize("dims", [(50, 12, 10, 2), (333, 50, 36, 1), (300, 32, 64, 2)], ids=["H10_L2", "H36_L1", "H64_L2"])
+def test_sampling_many_steps_small_and_stacked_models(torch_cuda, dims, flags):
+    """64 decode steps (4 graph replays of 16) on small / two-layer / H % 4 != 0 models: every token teacher-forced against the
+    fp64 oracle.  The decode-step GEMMs accumulate into buffers that the cell / argmax kernels must leave zeroed — a consumer that
+    does not (the scalar cell kernel once did not) only shows after a few steps."""
+    v, e, h, layers = dims
+    cfg = dict(name="lstm_baseline", input_size=v, embedding_size=e, hidden_size=h, n_layers=layers, max_len=8)
+    params = O.glorot_init(cfg, 1234)
+    eng = make_engine(cfg, 8, flags)
+    eng.load_params(params)
+    got = eng.sample_host(5, 64)
+    assert (got == got[0:1]).all()
+    assert_greedy(params, got[0], O.sample_greedy(params, 64, np.float64))
+    again = eng.sample_host(3, 40)                    # second call, other batch size: buffers re-zeroed, graphs re-captured
+    assert (again[0] == got[0, :40]).all()
+    eng.close()
+
+
 def _plugin_config(tmpdir=None, **over):
     cfg = dict(name="lstm_baseline", model_module_name="models.lstm_baseline", model_class_name="LSTMBaseline",
                input_size=200, embedding_size=32, hidden_size=32, n_layers=1, max_len=12, lr=5e-3, n_decay=10000,
