@@ -117,6 +117,8 @@ struct fsmg_handle {
     int overlap = 1;
     int dws_transposed = 1;  // softmax_w gradient accumulated as [V', H] (FSMG_DWS_T=0: [H, V'])
     int strip_overlap = 0;   // background softmax-gradient pass beside the dH / dWs GEMMs (FSMG_STRIP_OVERLAP=1; measured slower)
+    int fused_sg = 0;        // softmax gradient rebuilt inside the dH / dWs GEMMs from stored exponentials (FSMG_FUSED_SG; no HBM pass)
+    float* cmaxT = nullptr;  // [ceil(V'/16), chunk_rows] per-(16-column chunk, row) maxima of the logits chunk (fused softmax gradient)
     int samp_max = 0;
     // pinned host staging
     int32_t* h_tok = nullptr;
@@ -221,6 +223,7 @@ static void carve(fsmg_handle* h, char* base) {
     const char* env_dt = getenv("FSMG_DWS_T");
     if (env_dt) h->dws_transposed = atoi(env_dt);
     const char* env_so = getenv("FSMG_STRIP_OVERLAP");
+    { const char* env_fs = getenv("FSMG_FUSED_SG"); h->fused_sg = env_fs ? atoi(env_fs) : 0; }
     h->strip_overlap = env_so ? atoi(env_so) : 0;   // measured: 14.17 ms (1 background CTA/SM: 1.2 TB/s) / 12.65 (6/SM) vs 12.47 serial
     h->use_graph = env_gr ? atoi(env_gr) : 1;
     h->overlap = env_ov ? atoi(env_ov) : 0;   // measured: with 256 MB chunks and stream-K balanced GEMMs, overlapping streams lose (16.97 vs 14.35 ms)
@@ -245,6 +248,7 @@ static void carve(fsmg_handle* h, char* base) {
     h->dlogits = b.take<__half>(rows * h->Vp);
     h->dlogits_b[0] = h->dlogits;
     h->dlogits_b[1] = b.take<__half>(rows * h->Vp);
+    h->cmaxT = b.take<float>((int64_t)cdiv(h->V1, 16) * rows);
     // dWs accumulated with 16-byte aligned rows (V' is odd): [H, Vp], or transposed [V', Hq] (default, see projection())
     { int64_t a = (int64_t)h->H * h->Vp, bt = (int64_t)h->V1 * round_up(h->H, 4); h->dws_acc = b.take<float>(a > bt ? a : bt); }
     // sampler (fp32 route)
@@ -511,21 +515,29 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
             FSMG_CUDA_OK(cudaStreamWaitEvent(s, h->ev_dws[buf], 0));
         }
         int rc;
+        // Fused softmax gradient (FSMG_FUSED_SG): the logits GEMM leaves e = exp(logit - chunk max) in the fp16 chunk and the two
+        // consumer GEMMs rebuild softmax - onehot on the tiles TMA lands in their shared memory (tc_gemm_kernel "XF"): the in-place
+        // HBM pass over the chunk and its 4 B per logit of traffic disappear.  Needs the 256 x 512 pair-tile plan for both GEMMs.
+        const GemmArgs g_dh = mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H);
+        const GemmArgs g_dws = mk(h->V1, H, mc, h->dlogits, h->Vp, hc, h->Hp, h->dws_acc, Hq, loss_scale, nullptr, 0, 0, 1);
+        const bool fused = train && use_tc && h->fused_sg && dws_t && !overlap && tc_xf_supported(h->tc, g_dh) && tc_xf_supported(h->tc, g_dws);
+        XfArgs xf;
+        xf.cmaxT = h->cmaxT; xf.ld_cmax = h->chunk_rows; xf.n_c16 = cdiv(h->V1, 16); xf.lse = h->lse; xf.y = h->y_ids; xf.row0 = r0; xf.db = nullptr;
         if (use_tc) {
             // fused: logits tile -> online (max,sumexp) partials + target logit; fp16 logits only when training
             int n_part = 0;
             {
                 ProfScope ps(h, PH_PROJ_FWD, s);
                 rc = tc_projection_gemm(h->tc, hc, h->Hp, h->WsT16, h->Hp, sb, h->y_ids, r0, mc, H, h->V1,
-                                        train ? h->dlogits : nullptr, h->Vp, &n_part, s);
+                                        train ? h->dlogits : nullptr, h->Vp, &n_part, s, fused ? h->cmaxT : nullptr, h->chunk_rows);
             }
             if (rc) return rc;
             {
                 ProfScope ps(h, PH_SOFTMAX_GRAD, s);
-                rc = tc_projection_post(h->tc, n_part, h->y_ids, r0, mc, N, T, h->V1, train ? h->dlogits : nullptr, h->Vp, h->lse,
-                                        nll_out, loss_scale, g_sb, s);
+                rc = tc_projection_post(h->tc, n_part, h->y_ids, r0, mc, N, T, h->V1, (train && !fused) ? h->dlogits : nullptr, h->Vp,
+                                        h->lse, nll_out, loss_scale, g_sb, s);
             }
-            h->launches += train ? 3 : 2;
+            h->launches += (train && !fused) ? 3 : 2;
             if (rc) return rc;
         } else {
             ProfScope ps(h, PH_PROJ_FWD, s);
@@ -553,14 +565,16 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
         // dH[chunk] = dlogits * Ws^T   (unscaled; fp32)
         {
             ProfScope ps(h, PH_DH, s_dh);
-            rc = gemm_f16(h, mk(mc, H, h->V1, h->dlogits, h->Vp, h->Ws16, h->Vp, h->dact[0] + r0 * H, H), false, false, s_dh);
+            if (fused) { LAUNCH_COUNT(h); rc = tc_gemm(h->tc, g_dh, false, false, s_dh, &xf); }
+            else rc = gemm_f16(h, g_dh, false, false, s_dh);
         }
         if (rc) return rc;
         // dWs += loss_scale * hs_chunk^T * dlogits   (contraction over the chunk's tokens)
         {
             ProfScope ps_dws(h, PH_DWS, s_dws);
             // accumulated across chunks with fire-and-forget vector reductions into the L2-resident buffer (no read latency in the epilogue)
-            rc = dws_gemm(hc, h->dlogits, mc, s_dws);
+            if (fused) { xf.db = g_sb; LAUNCH_COUNT(h); rc = tc_gemm(h->tc, g_dws, true, true, s_dws, &xf); }   // + bias gradient
+            else rc = dws_gemm(hc, h->dlogits, mc, s_dws);
         }
         if (rc) return rc;
         if (overlap) {
@@ -1262,6 +1276,29 @@ int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const 
     if (rc) return rc;
     if (!tc_gemm_supported(g, a_mn_major != 0, b_mn_major != 0)) return set_error(FSMG_ERR_INVALID, "shape unsupported by the tcgen05 GEMM");
     return tc_gemm(ctx, g, a_mn_major != 0, b_mn_major != 0, s);
+}
+
+// the two projection-backward GEMMs with the softmax gradient rebuilt on their A operand in shared memory (tc_gemm_kernel "XF"),
+// on caller-provided buffers: parity test of the transform on its own.  a_mn_major = 0: C[M,N] = dl[M,K] * B[N,K]^T with
+// dl[r, v] = E[r, v] * exp(cmaxT[v / 16, r] - lse[r]) - (v == y[r]) (M token rows, K vocabulary); a_mn_major = 1: C[M,N] +=
+// alpha * dl^T * B with E stored [K tokens, lda >= M vocabulary], B stored [K tokens, ldb >= N], db[v] += alpha * column sums
+// of dl (C and db are accumulated atomically: the caller zeroes them).
+int fsmg_debug_gemm_xf(int32_t m, int32_t n, int32_t k, const void* d_e_f16, int64_t lda, const void* d_b_f16, int64_t ldb, float* d_c,
+                       int32_t a_mn_major, const float* d_cmaxT, int64_t ld_cmax, const float* d_lse, const int32_t* d_y, float alpha,
+                       float* d_db, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (m <= 0 || n <= 0 || k <= 0 || !d_e_f16 || !d_b_f16 || !d_c || !d_cmaxT || !d_lse || !d_y)
+        return set_error(FSMG_ERR_INVALID, "fsmg_debug_gemm_xf: bad argument");
+    GemmArgs g = a_mn_major ? mk(m, n, k, d_e_f16, lda, d_b_f16, ldb, d_c, n, alpha, nullptr, 0, 0, 1)
+                            : mk(m, n, k, d_e_f16, lda, d_b_f16, ldb, d_c, n);
+    static fsmg::TcContext ctx;
+    int rc = tc_init(ctx);
+    if (rc) return rc;
+    if (!tc_xf_supported(ctx, g)) return set_error(FSMG_ERR_INVALID, "shape has no 256 x 512 pair-tile plan");
+    XfArgs xf;
+    xf.cmaxT = d_cmaxT; xf.ld_cmax = ld_cmax; xf.n_c16 = cdiv(a_mn_major ? m : k, 16); xf.lse = d_lse; xf.y = d_y; xf.row0 = 0;
+    xf.db = a_mn_major ? d_db : nullptr;
+    return tc_gemm(ctx, g, a_mn_major != 0, a_mn_major != 0, s, &xf);
 }
 
 // one in-place softmax-gradient pass (dlogits = exp(logit - lse) - onehot(y), db += alpha * column sums) over a caller-provided

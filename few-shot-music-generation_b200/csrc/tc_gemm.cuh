@@ -261,6 +261,13 @@ struct EpiParams {
     const int32_t* y; int64_t row0;     // y[row0 + row]
     float* tgt;                         // tgt[row]
     __half* logits16; int64_t ld16;
+    // fused softmax gradient (see "XF" below).  EPI_LSE with exp_store: the fp16 chunk receives e = exp(logit - cmax) of every
+    // 16-column chunk instead of the logit, and cmax goes to cmaxT[(col / 16) * ld_cmax + row].  EPI_STORE with XF: the consumer
+    // GEMMs rebuild dlogits = e * exp(cmax - lse) - onehot(y) in shared memory (lse / y indexed by row0 + chunk row).
+    int exp_store;
+    float* cmaxT; int64_t ld_cmax; int n_c16;
+    const float* xf_lse;
+    float* xf_db;                       // XF = 2: db[col] += alpha * column sums of dlogits (pieces of N tile 0 only)
 };
 
 struct GemmShape {
@@ -363,12 +370,23 @@ struct SmemLayout {
 // rows of A and only HALF of the B tile, the tensor cores read both CTAs' shared memory.  The K-streaming mainloop is bound by the
 // bytes that must LAND in each SM's smem (measured ~40 B/clk/SM; a 1-SM 128 x 256 tile needs 96 B/clk at full tensor rate) —
 // TMA multicast (the previous CL = 2 scheme) cut L2 reads but not that ingest; the 2-SM MMA cuts it by a third.
-template <int BN, int EPI, bool A_MN, bool B_MN, int CL, bool ASTAT = false>
+//
+// XF (fused softmax gradient; cta_group::2 only).  The A operand of the two projection-backward GEMMs is dlogits = softmax - onehot.
+// Instead of a separate HBM pass that rewrites the fp16 logits chunk in place, the logits GEMM stores e = exp(logit - cmax) per
+// 16-column chunk (its epilogue computes those exponentials anyway) and the consumers finish the job on the tile that TMA has just
+// landed: A loads complete on a CTA-LOCAL barrier (raw_full), the sixteen epilogue warps — idle during the K loop of the
+// single-buffered 256 x 512 tiles — multiply every 32-byte piece by its row's exp(cmax - lse) (one MUFU per 16 elements), subtract
+// the one-hot target, fence the generic writes for the async proxy and arrive on the leader's full barrier next to the TMA bytes of
+// B.  XF = 1: A K-major (dH = dlogits * Ws^T: smem row = token, 128-byte row = one 64-column k block).  XF = 2: A MN-major
+// (dWs^T = dlogits^T * hs: smem row = token of the k block, two 64-column boxes); each thread owns fixed vocabulary columns there,
+// so the bias gradient (column sums of dlogits) accumulates in registers and leaves with a few REDs per work item.
+template <int BN, int EPI, bool A_MN, bool B_MN, int CL, bool ASTAT = false, int XF = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, GemmShape sh, EpiParams ep) {
     using L = SmemLayout<BN, CL, ASTAT>;
     using Iter = std::conditional_t<ASTAT, AstatIter, WorkIterFlags>;
     static_assert(!ASTAT || (CL == 2 && !A_MN && !B_MN && BN <= 256), "A-stationary schedule: K-major operands, cta_group::2");
+    static_assert(XF == 0 || (CL == 2 && !ASTAT && EPI == EPI_STORE && (XF == 1 ? !A_MN : A_MN)), "operand transform: pair tiles, plain-store epilogue");
     constexpr int STAGES = L::STAGES;
     // BN = 512 (cta_group::2 only): the pair's tile is 256 x 512, issued as two N = 256 MMAs per K step.  A is fetched once for the
     // whole 512-wide N extent (the L2 -> SM operand traffic, not the tensor pipe, bounds the large-K GEMMs) and the accumulator
@@ -391,8 +409,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* tmem_empty = tmem_full + 2;       // [2]
     uint64_t* a_full = tmem_empty + 2;          // [ASTAT_KB] ASTAT: panel kb of the current item has landed (leader: both CTAs' bytes)
     uint64_t* a_empty = a_full + ASTAT_KB;      // [ASTAT_KB] ASTAT: the item's last MMAs on panel kb have retired
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(a_empty + ASTAT_KB);
-    static_assert((2 * 8 + 4 + 2 * ASTAT_KB) * 8 + 8 <= L::BAR_BYTES, "barrier block");
+    uint64_t* raw_full = a_empty + ASTAT_KB;    // [STAGES] XF: this CTA's A tile of the stage has landed (CTA-local)
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(raw_full + 8);
+    static_assert((3 * 8 + 4 + 2 * ASTAT_KB) * 8 + 8 <= L::BAR_BYTES, "barrier block");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cta_rank = (CL == 2) ? (int)cluster_ctarank() : 0;
@@ -404,7 +423,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tma_prefetch_desc(&map_b);
         // CL = 2 (cta_group::2): the leader's full barrier collects both CTAs' TMA bytes, its tmem_empty both CTAs' epilogue warps;
         // empty / tmem_full are signalled in both CTAs by the leader's multicast tcgen05.commit
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        // XF: the leader's full barrier additionally collects one arrival per transform warp of both CTAs
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], XF ? 1 + CL * NUM_EPI_WARPS : 1); mbar_init(&empty_bar[i], 1); }
+        if (XF) for (int i = 0; i < STAGES; ++i) mbar_init(&raw_full[i], 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], CL * NUM_EPI_WARPS); }
         if (ASTAT) for (int i = 0; i < ASTAT_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         fence_barrier_init();
@@ -459,12 +480,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     } else {
                         // cta_group::2: this CTA streams ITS 128 rows of A and ITS half of the B tile (the tensor core reads both CTAs'
                         // smem); every load completes on the leader's barrier, which therefore expects both CTAs' bytes
-                        if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
-                        if (A_MN) {
+                        if (XF) {
+                            // A goes through this CTA's transform warps first: its bytes complete on the local raw_full barrier
+                            mbar_expect_tx(&raw_full[stage], L::A_BYTES);
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (L::STAGE_BYTES - L::A_BYTES));
+                            if (A_MN) {
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &full_bar[stage]);
+                                for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &raw_full[stage]);
+                            } else {
+                                tma_load_2d(sa, &map_a, kb * BK, m_blk * BM, &raw_full[stage]);
+                            }
                         } else {
-                            tma_load_2d_2sm(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+                            if (A_MN) {
+#pragma unroll
+                                for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * 8192, &map_a, m_blk * BM + j * 64, kb * BK, &full_bar[stage]);
+                            } else {
+                                tma_load_2d_2sm(sa, &map_a, kb * BK, m_blk * BM, &full_bar[stage]);
+                            }
                         }
                         // MMA j covers N columns [j * MMA_N, (j + 1) * MMA_N) of the tile; this CTA supplies its half of each
 #pragma unroll
@@ -540,10 +573,113 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         uint4* sh4 = reinterpret_cast<uint4*>(stg);              // fp16 staging: 32 rows x 2 uint4, slot c2 ^ ((row >> 2) & 1)
         float* bias_s = reinterpret_cast<float*>(stg + 1024);    // EPI_LSE: bias of this warp's GCOLS columns
         int acc = 0; uint32_t acc_phase = 0;
+        int xstage = 0; uint32_t xphase = 0;                     // XF: position in the operand ring (same walk as producer / MMA)
         Iter it(sh, cluster_id, n_clusters);
         int tile_mn, kb0, kb1;
         while (it.next(sh, tile_mn, kb0, kb1)) {
             const int m_blk = (tile_mn % sh.n_mp) * CL + cta_rank, n_blk = tile_mn / sh.n_mp;
+            if constexpr (XF != 0) {
+                // ===== operand transform: this CTA's A tile of every k block, in place, before the MMA may read it =====
+                // 512 threads x 32 bytes = the 128 smem rows x 128 bytes of the tile.  Thread -> smem row R, 16-column chunk c4 of
+                // the row (two 16-byte units; SWIZZLE_128B keeps a unit intact and moves it to slot unit ^ (R & 7)).
+                const int te = (int)threadIdx.x - 64;
+                const int R = te >> 2, c4 = te & 3;
+                const uint32_t off0 = (uint32_t)R * 128u + ((uint32_t)((2 * c4) ^ (R & 7)) << 4);
+                const uint32_t off1 = (uint32_t)R * 128u + ((uint32_t)((2 * c4 + 1) ^ (R & 7)) << 4);
+                constexpr float L2E = 1.4426950408889634f;
+                // XF = 1: R = token row of the tile (fixed for the item), chunk = kb * 4 + c4 walks with kb
+                // XF = 2: R = (box j = R >> 6, token kk = R & 63 of the k block), chunk = (m_blk * 128 + j * 64) / 16 + c4 fixed
+                const int xrow = m_blk * BM + R;                              // XF = 1: chunk-local token row
+                const int xcol0 = m_blk * BM + (R >> 6) * 64 + c4 * 16;       // XF = 2: first vocabulary column of this thread
+                float nlse = 0.0f; int ytok = -1; bool xok = false;           // XF = 1: per item
+                if (XF == 1) {
+                    xok = xrow < sh.M;
+                    if (xok) { nlse = -__ldg(ep.xf_lse + ep.row0 + xrow) * L2E; ytok = __ldg(ep.y + ep.row0 + xrow); }
+                }
+                float csum[16];
+                if (XF == 2) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) csum[e] = 0.0f;
+                }
+                // operands of the first k block; inside the loop the next block's are fetched before the wait
+                float cm_n = 0.0f, ls_n = 0.0f; int y_n = -1; bool ok_n = false;
+                auto fetch = [&](int kb) {
+                    if (XF == 1) {
+                        const int c16 = kb * 4 + c4;
+                        ok_n = xok && c16 < ep.n_c16;
+                        if (ok_n) cm_n = __ldg(ep.cmaxT + (int64_t)c16 * ep.ld_cmax + xrow);
+                    } else {
+                        const int tok = kb * BK + (R & 63);
+                        const int c16 = xcol0 >> 4;
+                        ok_n = tok < sh.K && c16 < ep.n_c16;
+                        if (ok_n) {
+                            cm_n = __ldg(ep.cmaxT + (int64_t)c16 * ep.ld_cmax + tok);
+                            ls_n = __ldg(ep.xf_lse + ep.row0 + tok);
+                            y_n = __ldg(ep.y + ep.row0 + tok);
+                        }
+                    }
+                };
+                fetch(kb0);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    const float cm = cm_n, ls = ls_n; const int yv = y_n; const bool ok = ok_n;
+                    if (kb + 1 < kb1) fetch(kb + 1);
+                    mbar_wait(&raw_full[xstage], xphase);
+                    uint8_t* sa = ring + xstage * L::STAGE_BYTES;
+                    uint4 u0 = *reinterpret_cast<uint4*>(sa + off0);
+                    uint4 u1 = *reinterpret_cast<uint4*>(sa + off1);
+                    // scale of this (row, 16-column chunk): exp(cmax - lse), rounded to fp16 like the operand it multiplies
+                    const float sc = ok ? fast_ex2(XF == 1 ? fmaf(cm, L2E, nlse) : (cm - ls) * L2E) : 0.0f;
+                    const __half2 s2 = __float2half2_rn(sc);
+                    __half2* h0 = reinterpret_cast<__half2*>(&u0);
+                    __half2* h1 = reinterpret_cast<__half2*>(&u1);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { h0[q] = __hmul2(h0[q], s2); h1[q] = __hmul2(h1[q], s2); }
+                    // one-hot target: column (XF = 1: ytok - kb * 64, XF = 2: y - first column of the box) relative to this chunk
+                    const int tc16 = (XF == 1 ? ytok - kb * BK : yv - (m_blk * BM + (R >> 6) * 64)) - c4 * 16;
+                    if (ok && (unsigned)tc16 < 16u) {
+                        const __half one = __float2half_rn(1.0f);
+                        __half* a0 = reinterpret_cast<__half*>(&u0);
+                        __half* a1 = reinterpret_cast<__half*>(&u1);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (tc16 == e) a0[e] = __hsub(a0[e], one);
+                            if (tc16 == 8 + e) a1[e] = __hsub(a1[e], one);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(sa + off0) = u0;
+                    *reinterpret_cast<uint4*>(sa + off1) = u1;
+                    if (XF == 2) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 f0 = __half22float2(h0[q]), f1 = __half22float2(h1[q]);
+                            csum[2 * q] += f0.x; csum[2 * q + 1] += f0.y;
+                            csum[8 + 2 * q] += f1.x; csum[8 + 2 * q + 1] += f1.y;
+                        }
+                    }
+                    fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (cta_rank == 1) mbar_arrive_remote(&full_bar[xstage], 0); else mbar_arrive(&full_bar[xstage]);
+                    }
+                    if (++xstage == STAGES) { xstage = 0; xphase ^= 1; }
+                }
+                if (XF == 2 && ep.xf_db != nullptr && n_blk == 0) {
+                    // column sums over this piece's tokens: lanes of a warp that share (te & 3) hold the same columns for 8 tokens
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        float v = csum[e];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        csum[e] = v;
+                    }
+                    if (lane < 4) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e)
+                            if (xcol0 + e < sh.M) atomicAdd(ep.xf_db + xcol0 + e, ep.alpha * csum[e]);
+                    }
+                }
+            }
             const int row_w0 = m_blk * BM + quad * 32;            // first row of this warp
             const int row = row_w0 + lane;                         // row held by this thread in TMEM
             const bool row_ok = row < sh.M;
@@ -742,12 +878,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     const float nmax_l2 = cmax * 1.4426950408889634f;
                     float sa0 = 0.0f, sa1 = 0.0f, sa2 = 0.0f, sa3 = 0.0f;   // independent chains
+                    if (ep.exp_store) {
+                        // fused softmax gradient: the chunk buffer receives the exponentials (in (0, 1], the chunk's largest = 1) and
+                        // the consumers rescale them by exp(cmax - lse); v[] is dead after the target pick above
 #pragma unroll
-                    for (int j = 0; j < CW; j += 4) {
-                        sa0 += fast_ex2(fmaf(v[j], 1.4426950408889634f, -nmax_l2));          // one FFMA + MUFU.EX2 per logit
-                        sa1 += fast_ex2(fmaf(v[j + 1], 1.4426950408889634f, -nmax_l2));
-                        sa2 += fast_ex2(fmaf(v[j + 2], 1.4426950408889634f, -nmax_l2));
-                        sa3 += fast_ex2(fmaf(v[j + 3], 1.4426950408889634f, -nmax_l2));
+                        for (int j = 0; j < CW; j += 4) {
+                            v[j] = fast_ex2(fmaf(v[j], 1.4426950408889634f, -nmax_l2));
+                            v[j + 1] = fast_ex2(fmaf(v[j + 1], 1.4426950408889634f, -nmax_l2));
+                            v[j + 2] = fast_ex2(fmaf(v[j + 2], 1.4426950408889634f, -nmax_l2));
+                            v[j + 3] = fast_ex2(fmaf(v[j + 3], 1.4426950408889634f, -nmax_l2));
+                            sa0 += v[j]; sa1 += v[j + 1]; sa2 += v[j + 2]; sa3 += v[j + 3];
+                        }
+                        if (row_ok) ep.cmaxT[(int64_t)(col0 >> 4) * ep.ld_cmax + row] = cmax;   // 32 rows of a warp: one 128-byte line
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; j += 4) {
+                            sa0 += fast_ex2(fmaf(v[j], 1.4426950408889634f, -nmax_l2));          // one FFMA + MUFU.EX2 per logit
+                            sa1 += fast_ex2(fmaf(v[j + 1], 1.4426950408889634f, -nmax_l2));
+                            sa2 += fast_ex2(fmaf(v[j + 2], 1.4426950408889634f, -nmax_l2));
+                            sa3 += fast_ex2(fmaf(v[j + 3], 1.4426950408889634f, -nmax_l2));
+                        }
                     }
                     cmx[cc] = cmax;
                     csm[cc] = (sa0 + sa1) + (sa2 + sa3);
@@ -1142,6 +1292,8 @@ static inline int tc_init(TcContext& c) {
                                       tc::SmemLayout<BN, 2>::TOTAL))
     FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<512, tc::EPI_STORE, false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<512, 2>::TOTAL));
     FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<512, tc::EPI_STORE, true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<512, 2>::TOTAL));
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<512, tc::EPI_STORE, false, false, 2, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<512, 2>::TOTAL));
+    FSMG_CUDA_OK(cudaFuncSetAttribute(tc::tc_gemm_kernel<512, tc::EPI_STORE, true, true, 2, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SmemLayout<512, 2>::TOTAL));
     FSMG_SET_SMEM(256, tc::EPI_STORE, false, false);
     FSMG_SET_SMEM(256, tc::EPI_STORE, true, true);
     FSMG_SET_SMEM(128, tc::EPI_STORE, false, false);
@@ -1292,7 +1444,23 @@ static inline int tc_make_maps(const TcContext& c, const GemmArgs& g, bool mn, i
     return 0;
 }
 
-static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn, cudaStream_t s) {
+// fused softmax gradient: what the consumer GEMMs need to rebuild dlogits from the exponentials chunk (tc_gemm_kernel, "XF")
+struct XfArgs {
+    const float* cmaxT; int64_t ld_cmax; int n_c16;   // per (16-column chunk, chunk row) maximum written by the logits GEMM
+    const float* lse; const int32_t* y; int64_t row0; // per token of the step: log-sum-exp, target id; first token of the chunk
+    float* db;                                        // softmax_b gradient (dWs GEMM only)
+};
+
+// the transform variants exist for the 256 x 512 pair tiles only (long K loops, single-buffered accumulator: idle epilogue warps)
+static inline bool tc_xf_supported(const TcContext& c, const GemmArgs& g) {
+    if (!c.ready || !c.enabled) return false;
+    if (!tc_operands_ok(g.A, g.lda) || !tc_operands_ok(g.B, g.ldb)) return false;
+    const bool can_split = !g.c_half && !g.accumulate;
+    const TcPlan p = tc_plan(c, g.M, g.N, g.K, can_split, 0, true);
+    return p.bn == 512 && p.cl == 2;
+}
+
+static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn, cudaStream_t s, const XfArgs* xf = nullptr) {
     (void)b_mn;
     if (!c.ready) return set_error(-3, "tcgen05 context not initialised");
     const bool can_split = !g.c_half && !g.accumulate;   // split-K partials are combined with fp32 atomics
@@ -1302,6 +1470,11 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
     ep.C = g.C; ep.ldc = g.ldc; ep.bias = g.bias; ep.alpha = g.alpha; ep.c_half = g.c_half; ep.accumulate = g.accumulate;
     ep.atomic = g.atomic;
     ep.vec_ok = ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0 && (g.ldc % 4) == 0) ? 1 : 0;
+    if (xf) {
+        if (p.bn != 512 || p.cl != 2) return set_error(-1, "operand-transform GEMM needs a 256 x 512 pair-tile plan (M=%d N=%d K=%d)", g.M, g.N, g.K);
+        ep.cmaxT = const_cast<float*>(xf->cmaxT); ep.ld_cmax = xf->ld_cmax; ep.n_c16 = xf->n_c16;
+        ep.xf_lse = xf->lse; ep.y = xf->y; ep.row0 = xf->row0; ep.xf_db = xf->db;
+    }
     if (p.sh.n_s > 1 && !g.atomic) {
         // plain store with split-K: zero the destination, then accumulate atomically
         FSMG_CUDA_OK(cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s));
@@ -1310,6 +1483,13 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
     CUtensorMap ma, mb;
     int rc = tc_make_maps(c, g, a_mn, p.bn, p.cl, &ma, &mb);
     if (rc) return rc;
+    if (xf) {
+        rc = !a_mn ? tc_launch_kernel(tc::tc_gemm_kernel<512, tc::EPI_STORE, false, false, 2, false, 1>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s)
+                   : tc_launch_kernel(tc::tc_gemm_kernel<512, tc::EPI_STORE, true, true, 2, false, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s);
+        if (rc) return rc;
+        FSMG_LAUNCH_OK();
+        return 0;
+    }
     return tc_launch<tc::EPI_STORE>(c, p, ma, mb, a_mn, ep, s);
 }
 
@@ -1337,7 +1517,7 @@ static inline bool tc_projection_supported(TcContext& c, int H, int V1) {
 
 static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh, const __half* WsT16, int64_t ldw, const float* sb,
                                      const int32_t* y, int64_t row0, int mc, int H, int V1, __half* logits16, int64_t ld16,
-                                     int* n_part_out, cudaStream_t s) {
+                                     int* n_part_out, cudaStream_t s, float* cmaxT = nullptr, int64_t ld_cmax = 0) {
     GemmArgs g;
     memset(&g, 0, sizeof g);
     g.M = mc; g.N = V1; g.K = H; g.A = hc; g.lda = ldh; g.B = WsT16; g.ldb = ldw;
@@ -1348,6 +1528,7 @@ static inline int tc_projection_gemm(TcContext& c, const __half* hc, int64_t ldh
     memset(&ep, 0, sizeof ep);
     ep.bias = sb; ep.part = c.part; ep.n_tiles_total = 4 * p.sh.n_n; ep.y = y; ep.row0 = row0; ep.tgt = c.tgt;
     ep.logits16 = logits16; ep.ld16 = ld16;
+    ep.exp_store = (logits16 && cmaxT) ? 1 : 0; ep.cmaxT = cmaxT; ep.ld_cmax = ld_cmax; ep.n_c16 = cdiv(V1, 16);
     ep.vec_ok = (logits16 && (reinterpret_cast<uintptr_t>(logits16) & 31) == 0 && (ld16 % 16) == 0) ? 1 : 0;   // 256-bit row-chunk stores
     *n_part_out = 4 * p.sh.n_n;
     CUtensorMap ma, mb;

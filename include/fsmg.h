@@ -197,6 +197,16 @@ int fsmg_debug_softmax_grad(int32_t rows, int32_t vocab1, int64_t ld, void* d_lo
                             const int32_t* d_y, float alpha, float* d_db, int32_t mode, int32_t param, int32_t waves,
                             void* stream);
 
+/* The projection-backward GEMMs with the softmax gradient rebuilt on their A operand inside the kernel (no HBM pass; reference
+ * lstm_baseline.py:70-75 + tf.gradients through sequence_loss and xw_plus_b), on caller-provided device buffers: test hook.
+ * E holds exp(logit - max of the logit's 16-column chunk) in fp16, cmaxT[chunk, row] those maxima, lse/y the per-row
+ * log-sum-exp / target.  a_mn_major = 0: C[M,N] = dl * B[N,K]^T, dl[r, v] = E[r, v] * exp(cmaxT[v / 16, r] - lse[r]) - (v == y[r])
+ * (M rows, K vocabulary).  a_mn_major = 1: C[M,N] += alpha * dl^T * B with E stored [K rows, lda >= M vocabulary], B stored
+ * [K rows, ldb >= N]; db[v] += alpha * column sums of dl (caller zeroes C and db). */
+int fsmg_debug_gemm_xf(int32_t m, int32_t n, int32_t k, const void* d_e_f16, int64_t lda, const void* d_b_f16, int64_t ldb,
+                       float* d_c, int32_t a_mn_major, const float* d_cmaxT, int64_t ld_cmax, const float* d_lse,
+                       const int32_t* d_y, float alpha, float* d_db, void* stream);
+
 /* ---- device-side episode assembly (replaces the host loop of EpisodeSampler.get_episode, reference
  * src/data/episode.py:62-74, once the tokenised corpus is resident in HBM) ---------------------------------------------
  * d_corpus is int32 [n_corpus_rows, row_len] (every song of the split, zero-padded to max_len like
