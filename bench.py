@@ -196,7 +196,7 @@ def run_reference(args, w, wname):
 
 def kernel_traffic() -> dict:
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernels, from the committed `ncu --set full` captures."""
-    for name in ("r2_traffic.json", "r1_traffic.json"):
+    for name in ("r3_traffic.json", "r2_traffic.json", "r1_traffic.json"):
         f = ROOT / "profiles" / name
         if f.exists():
             try:
@@ -379,24 +379,34 @@ def measure_training(args, wname: str, w: dict, steps: int, warmup: int, world: 
             r["note"] = note
         return r
 
+    # fused softmax gradient (default): the in-place HBM pass over the logits chunk no longer exists — the `softmax_grad_bias`
+    # bracket then holds only lse_combine (per-row merge of the (max, sum exp) partials)
+    fused_sg = os.environ.get("FSMG_FUSED_SG", "1") != "0" and brackets.get("softmax_grad_bias", 0) > 0 \
+        and phases.get("softmax_grad_bias", 0.0) < 0.5 * phases.get("proj_dh", 1e9)
     rec_flops = 2.0 * tok_gpu * h_ * 4 * h_          # h_{t-1} * Wh (forward) / dgates_{t+1} * Wh^T (backward): 2*H*4H per token
     rec_note = "sequential T-step recurrence: the bound is the per-step exchange latency, not the tensor pipe (DESIGN.md §5 R)"
     roof = {
         "recurrent_bwd": tensor_roofline("recurrent_bwd", "tc::lstm_bwd_* persistent reverse-time recurrence (dgates exchange, W_hh^T slice SMEM-resident)", rec_flops, rec_note),
         "recurrent_fwd": tensor_roofline("recurrent_fwd", "tc::lstm_fwd_* persistent recurrence (h exchange, W_hh slice SMEM-resident)", rec_flops, rec_note),
         "proj_logits_lse": tensor_roofline("proj_logits_lse", "tc::tc_gemm_kernel<256, EPI_LSE> projection logits + online log-sum-exp", 2.0 * tok_gpu * h_ * v1_),
-        "proj_dh": tensor_roofline("proj_dh", "tc::tc_gemm_kernel<512> dH = dlogits * Ws^T", 2.0 * tok_gpu * h_ * v1_),
-        "proj_dws": tensor_roofline("proj_dws", "tc::tc_gemm_kernel<512, MN-major> dWs^T += dlogits^T * hs", 2.0 * tok_gpu * h_ * v1_),
+        "proj_dh": tensor_roofline("proj_dh", "tc::tc_gemm_kernel<512" + (", XF=1> dH = (softmax - onehot rebuilt in smem) * Ws^T" if fused_sg else "> dH = dlogits * Ws^T"), 2.0 * tok_gpu * h_ * v1_),
+        "proj_dws": tensor_roofline("proj_dws", "tc::tc_gemm_kernel<512, MN-major" + (", XF=2> dWs^T += (softmax - onehot rebuilt in smem)^T * hs, + bias gradient" if fused_sg else "> dWs^T += dlogits^T * hs"), 2.0 * tok_gpu * h_ * v1_),
     }
     # the bench line's `roofline` is the kernel that takes the most time in the step (by the phase brackets), whichever it is
     top = max(roof, key=lambda k: phases.get(k, 0.0))
     vp = (v1_ + 15) // 16 * 16
     sg_ms = phases.get("softmax_grad_bias", 0.0)
     sg_bytes = 2.0 * tok_gpu * vp * 2          # one read + one write of every fp16 logit
-    roofline_hbm = dict(bound="hbm", kernel="tc::softmax_grad_stream_kernel (+ lse_combine) in-place dlogits = softmax - onehot, bias-gradient column sums",
+    sg_kernel = "tc::softmax_grad_stream_kernel (+ lse_combine) in-place dlogits = softmax - onehot, bias-gradient column sums"
+    if fused_sg:
+        sg_bytes = tok_gpu * (4 * ((v1_ + 255) // 256) * 8 + 16)      # (max, sum exp) partials in, lse / nll out
+        sg_kernel = "tc::lse_combine_kernel (fused softmax gradient: no HBM pass over the logits; dlogits is rebuilt inside the dH / dWs GEMMs)"
+    roofline_hbm = dict(bound="hbm", kernel=sg_kernel,
                         achieved=sg_bytes / (sg_ms * 1e-3) / 1e9 if sg_ms > 0 else 0.0, peak=pk["hbm"], unit="GB/s",
                         frac=(sg_bytes / (sg_ms * 1e-3) / 1e9 / pk["hbm"]) if sg_ms > 0 else 0.0, ms_per_step=sg_ms,
                         traffic=traffic.get("softmax_grad_bias"))
+    if fused_sg:
+        roofline_hbm["traffic"] = None
     if phases.get("softmax_grad_bias", 0.0) > phases.get(top, 0.0):
         top_roofline = dict(roofline_hbm)
     else:

@@ -223,7 +223,7 @@ static void carve(fsmg_handle* h, char* base) {
     const char* env_dt = getenv("FSMG_DWS_T");
     if (env_dt) h->dws_transposed = atoi(env_dt);
     const char* env_so = getenv("FSMG_STRIP_OVERLAP");
-    { const char* env_fs = getenv("FSMG_FUSED_SG"); h->fused_sg = env_fs ? atoi(env_fs) : 0; }
+    { const char* env_fs = getenv("FSMG_FUSED_SG"); h->fused_sg = env_fs ? atoi(env_fs) : 1; }
     h->strip_overlap = env_so ? atoi(env_so) : 0;   // measured: 14.17 ms (1 background CTA/SM: 1.2 TB/s) / 12.65 (6/SM) vs 12.47 serial
     h->use_graph = env_gr ? atoi(env_gr) : 1;
     h->overlap = env_ov ? atoi(env_ov) : 0;   // measured: with 256 MB chunks and stream-K balanced GEMMs, overlapping streams lose (16.97 vs 14.35 ms)

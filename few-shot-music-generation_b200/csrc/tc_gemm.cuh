@@ -268,6 +268,7 @@ struct EpiParams {
     float* cmaxT; int64_t ld_cmax; int n_c16;
     const float* xf_lse;
     float* xf_db;                       // XF = 2: db[col] += alpha * column sums of dlogits (pieces of N tile 0 only)
+    int xf_diag;                        // timing diagnostics only (FSMG_XF_DIAG, wrong results): bit 0 no column sums, bit 1 no transform math
 };
 
 struct GemmShape {
@@ -601,67 +602,82 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int e = 0; e < 16; ++e) csum[e] = 0.0f;
                 }
-                // operands of the first k block; inside the loop the next block's are fetched before the wait
-                float cm_n = 0.0f, ls_n = 0.0f; int y_n = -1; bool ok_n = false;
-                auto fetch = [&](int kb) {
+                // Per-(row, chunk) scalars of a k block (chunk maximum; XF = 2 also the token's lse and target) come from global
+                // memory.  They are fetched TWO k blocks ahead, right after the arrive of the current one: a load still in flight
+                // would stall both its first use and the proxy fence (measured: 30 % of this loop's stall samples with a fetch
+                // one block ahead, issued before the wait) — this way every load has a whole k-block period to land.
+                struct XfOp { float cm, ls; int y; bool ok; };
+                auto fetch = [&](XfOp& o, int kb) {
+                    o.cm = 0.0f; o.ls = 0.0f; o.y = -1; o.ok = false;
+                    if (kb >= kb1) return;
                     if (XF == 1) {
                         const int c16 = kb * 4 + c4;
-                        ok_n = xok && c16 < ep.n_c16;
-                        if (ok_n) cm_n = __ldg(ep.cmaxT + (int64_t)c16 * ep.ld_cmax + xrow);
+                        o.ok = xok && c16 < ep.n_c16;
+                        if (o.ok) o.cm = __ldg(ep.cmaxT + (int64_t)c16 * ep.ld_cmax + xrow);
                     } else {
                         const int tok = kb * BK + (R & 63);
                         const int c16 = xcol0 >> 4;
-                        ok_n = tok < sh.K && c16 < ep.n_c16;
-                        if (ok_n) {
-                            cm_n = __ldg(ep.cmaxT + (int64_t)c16 * ep.ld_cmax + tok);
-                            ls_n = __ldg(ep.xf_lse + ep.row0 + tok);
-                            y_n = __ldg(ep.y + ep.row0 + tok);
+                        o.ok = tok < sh.K && c16 < ep.n_c16;
+                        if (o.ok) {
+                            o.cm = __ldg(ep.cmaxT + (int64_t)c16 * ep.ld_cmax + tok);
+                            o.ls = __ldg(ep.xf_lse + ep.row0 + tok);
+                            o.y = __ldg(ep.y + ep.row0 + tok);
                         }
                     }
                 };
-                fetch(kb0);
-                for (int kb = kb0; kb < kb1; ++kb) {
-                    const float cm = cm_n, ls = ls_n; const int yv = y_n; const bool ok = ok_n;
-                    if (kb + 1 < kb1) fetch(kb + 1);
+                auto process = [&](const XfOp& o, int kb) {
                     mbar_wait(&raw_full[xstage], xphase);
                     uint8_t* sa = ring + xstage * L::STAGE_BYTES;
-                    uint4 u0 = *reinterpret_cast<uint4*>(sa + off0);
-                    uint4 u1 = *reinterpret_cast<uint4*>(sa + off1);
-                    // scale of this (row, 16-column chunk): exp(cmax - lse), rounded to fp16 like the operand it multiplies
-                    const float sc = ok ? fast_ex2(XF == 1 ? fmaf(cm, L2E, nlse) : (cm - ls) * L2E) : 0.0f;
-                    const __half2 s2 = __float2half2_rn(sc);
-                    __half2* h0 = reinterpret_cast<__half2*>(&u0);
-                    __half2* h1 = reinterpret_cast<__half2*>(&u1);
+                    if (!(ep.xf_diag & 2)) {      // (diagnostics: bit 1 = barrier hand-over only)
+                        uint4 u0 = *reinterpret_cast<uint4*>(sa + off0);
+                        uint4 u1 = *reinterpret_cast<uint4*>(sa + off1);
+                        // scale of this (row, 16-column chunk): exp(cmax - lse), rounded to fp16 like the operand it multiplies
+                        const float sc = o.ok ? fast_ex2(XF == 1 ? fmaf(o.cm, L2E, nlse) : (o.cm - o.ls) * L2E) : 0.0f;
+                        const __half2 s2 = __float2half2_rn(sc);
+                        __half2* h0 = reinterpret_cast<__half2*>(&u0);
+                        __half2* h1 = reinterpret_cast<__half2*>(&u1);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) { h0[q] = __hmul2(h0[q], s2); h1[q] = __hmul2(h1[q], s2); }
-                    // one-hot target: column (XF = 1: ytok - kb * 64, XF = 2: y - first column of the box) relative to this chunk
-                    const int tc16 = (XF == 1 ? ytok - kb * BK : yv - (m_blk * BM + (R >> 6) * 64)) - c4 * 16;
-                    if (ok && (unsigned)tc16 < 16u) {
-                        const __half one = __float2half_rn(1.0f);
-                        __half* a0 = reinterpret_cast<__half*>(&u0);
-                        __half* a1 = reinterpret_cast<__half*>(&u1);
+                        for (int q = 0; q < 4; ++q) { h0[q] = __hmul2(h0[q], s2); h1[q] = __hmul2(h1[q], s2); }
+                        // one-hot target: column (XF = 1: ytok - kb * 64, XF = 2: y - first column of the box) relative to this chunk
+                        const int tc16 = (XF == 1 ? ytok - kb * BK : o.y - (m_blk * BM + (R >> 6) * 64)) - c4 * 16;
+                        if (o.ok && (unsigned)tc16 < 16u) {
+                            const __half one = __float2half_rn(1.0f);
+                            __half* a0 = reinterpret_cast<__half*>(&u0);
+                            __half* a1 = reinterpret_cast<__half*>(&u1);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            if (tc16 == e) a0[e] = __hsub(a0[e], one);
-                            if (tc16 == 8 + e) a1[e] = __hsub(a1[e], one);
+                            for (int e = 0; e < 8; ++e) {
+                                if (tc16 == e) a0[e] = __hsub(a0[e], one);
+                                if (tc16 == 8 + e) a1[e] = __hsub(a1[e], one);
+                            }
                         }
-                    }
-                    *reinterpret_cast<uint4*>(sa + off0) = u0;
-                    *reinterpret_cast<uint4*>(sa + off1) = u1;
-                    if (XF == 2) {
+                        *reinterpret_cast<uint4*>(sa + off0) = u0;
+                        *reinterpret_cast<uint4*>(sa + off1) = u1;
+                        if (XF == 2 && !(ep.xf_diag & 1)) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const float2 f0 = __half22float2(h0[q]), f1 = __half22float2(h1[q]);
-                            csum[2 * q] += f0.x; csum[2 * q + 1] += f0.y;
-                            csum[8 + 2 * q] += f1.x; csum[8 + 2 * q + 1] += f1.y;
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 f0 = __half22float2(h0[q]), f1 = __half22float2(h1[q]);
+                                csum[2 * q] += f0.x; csum[2 * q + 1] += f0.y;
+                                csum[8 + 2 * q] += f1.x; csum[8 + 2 * q + 1] += f1.y;
+                            }
                         }
+                        fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     }
-                    fence_proxy_async();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     __syncwarp();
                     if (lane == 0) {
                         if (cta_rank == 1) mbar_arrive_remote(&full_bar[xstage], 0); else mbar_arrive(&full_bar[xstage]);
                     }
                     if (++xstage == STAGES) { xstage = 0; xphase ^= 1; }
+                };
+                XfOp opA, opB;
+                fetch(opA, kb0);
+                fetch(opB, kb0 + 1);
+                for (int kb = kb0; kb < kb1; kb += 2) {
+                    process(opA, kb);
+                    fetch(opA, kb + 2);
+                    if (kb + 1 < kb1) {
+                        process(opB, kb + 1);
+                        fetch(opB, kb + 3);
+                    }
                 }
                 if (XF == 2 && ep.xf_db != nullptr && n_blk == 0) {
                     // column sums over this piece's tokens: lanes of a warp that share (te & 3) hold the same columns for 8 tokens
@@ -1225,6 +1241,7 @@ struct TcContext {
     int lstm_pub_cta = 0;      // forward split kernel: one release per (CTA, half) instead of per warp (FSMG_LSTM_PUB_CTA=1)
     int lstm_fks = 4;          // forward split kernel: K chunks per ring stage (FSMG_LSTM_FKS = 1, 2, 4)
     int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
+    int xf_diag = 0;           // FSMG_XF_DIAG: timing diagnostics of the operand-transform GEMMs (results are wrong when set)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
     int lstm_reserve_sms = 0;  // SMs the persistent recurrent kernels leave free (for the NCCL kernels of an overlapped gradient all-reduce)
 };
@@ -1251,6 +1268,8 @@ static inline int tc_init(TcContext& c) {
     c.astat = enva ? atoi(enva) : 0;
     const char* envw = getenv("FSMG_WIDE");
     c.wide = envw ? atoi(envw) : 1;
+    const char* envxd = getenv("FSMG_XF_DIAG");
+    c.xf_diag = envxd ? atoi(envxd) : 0;
     const char* envs = getenv("FSMG_STREAMK");
     c.streamk = envs ? atoi(envs) : 1;
     const char* envp = getenv("FSMG_LSTM_PAIR");
@@ -1473,7 +1492,7 @@ static inline int tc_gemm(TcContext& c, const GemmArgs& g, bool a_mn, bool b_mn,
     if (xf) {
         if (p.bn != 512 || p.cl != 2) return set_error(-1, "operand-transform GEMM needs a 256 x 512 pair-tile plan (M=%d N=%d K=%d)", g.M, g.N, g.K);
         ep.cmaxT = const_cast<float*>(xf->cmaxT); ep.ld_cmax = xf->ld_cmax; ep.n_c16 = xf->n_c16;
-        ep.xf_lse = xf->lse; ep.y = xf->y; ep.row0 = xf->row0; ep.xf_db = xf->db;
+        ep.xf_lse = xf->lse; ep.y = xf->y; ep.row0 = xf->row0; ep.xf_db = xf->db; ep.xf_diag = c.xf_diag;
     }
     if (p.sh.n_s > 1 && !g.atomic) {
         // plain store with split-K: zero the destination, then accumulate atomically
