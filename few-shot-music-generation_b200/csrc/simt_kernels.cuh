@@ -706,10 +706,21 @@ __global__ void split_weight_t_kernel(const float* __restrict__ in, int64_t ldi,
 
 // Sampler cell step: gates = G[n,:] (+ P[word[n],:] when P != null: the embedding row already multiplied by Wx, bias
 // included) -> c (in place, fp32) -> h -> split [hi | lo] for the next contractions.
+//
+// Programmatic dependent launch (decode loop, FSMG_SAMPLE_PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor still runs; griddep_wait() blocks until the predecessor has completed and its writes
+// are visible (a no-op for ordinary launches), griddep_launch() lets the successor's CTAs become resident behind this grid.
+// Every kernel of the decode step calls wait first and launch right after, so at most two grids overlap: the running one and the
+// next one's prologue (block scheduling, TMEM allocation, barrier initialisation, descriptor prefetch).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // scalar variant (one unit per thread) for hidden sizes that are not a multiple of 4
 __global__ void sample_cell_scalar_kernel(float* __restrict__ G, int64_t ldg, const float* __restrict__ P, int64_t ldp,
                                           const int32_t* __restrict__ words, const float* __restrict__ bias,
                                           float* __restrict__ c_state, __half* __restrict__ h_split, int Hp, int n, int H) {
+    griddep_wait();
+    griddep_launch();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * H) return;
     int r = (int)(idx / H), u = (int)(idx % H);
@@ -738,6 +749,8 @@ __global__ void sample_cell_kernel(float* __restrict__ G, int64_t ldg, const flo
                                    float* __restrict__ c_state, __half* __restrict__ h_split, int Hp, int n, int H) {
     // four consecutive units per thread (16-byte loads of the four gate blocks, the per-word table row and the cell state; 8-byte stores of
     // the three fp16 planes): 4x fewer threads, 4x the bytes in flight per thread.  H % 4 == 0 and 16-byte aligned rows are checked by the caller.
+    griddep_wait();
+    griddep_launch();
     const int H4 = H >> 2;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)n * H4) return;
@@ -789,6 +802,8 @@ __global__ void __launch_bounds__(256) argmax_rows_step_kernel(float* __restrict
                                                                int32_t* __restrict__ out, int64_t out_stride, int* __restrict__ step_counter) {
     __shared__ float sv[32];
     __shared__ int si[32];
+    griddep_wait();
+    griddep_launch();
     int r = blockIdx.x;
     float* row = logits + (int64_t)r * ld;       // consumed rows are left zeroed for the next step's accumulating GEMM
     float best = -INFINITY;

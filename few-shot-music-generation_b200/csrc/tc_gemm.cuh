@@ -437,6 +437,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (CL == 2) cluster_sync_all();      // peer barriers are initialised before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
+    // programmatic dependent launch (decode loop): everything above touched only this CTA's own state; operands, accumulation
+    // targets and epilogue inputs are read / written below, after the predecessor grid has completed (no-ops otherwise)
+    griddep_wait();
+    griddep_launch();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -1241,6 +1245,7 @@ struct TcContext {
     int lstm_pub_cta = 0;      // forward split kernel: one release per (CTA, half) instead of per warp (FSMG_LSTM_PUB_CTA=1)
     int lstm_fks = 4;          // forward split kernel: K chunks per ring stage (FSMG_LSTM_FKS = 1, 2, 4)
     int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
+    int pdl = 0;               // launch with programmatic stream serialization (set by the decode loop around its GEMMs)
     int xf_diag = 0;           // FSMG_XF_DIAG: timing diagnostics of the operand-transform GEMMs (results are wrong when set)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
     int lstm_reserve_sms = 0;  // SMs the persistent recurrent kernels leave free (for the NCCL kernels of an overlapped gradient all-reduce)
@@ -1413,18 +1418,27 @@ static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow
 
 template <typename K>
 static inline int tc_launch_kernel(K kernel, const TcPlan& p, int smem, const CUtensorMap& ma, const CUtensorMap& mb,
-                                   const tc::EpiParams& ep, cudaStream_t s) {
+                                   const tc::EpiParams& ep, cudaStream_t s, int pdl = 0) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(p.grid);
     cfg.blockDim = dim3(tc::NUM_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (p.cl > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = p.cl; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = p.cl > 1 ? 1 : 0;
+    cfg.numAttrs = na;
     FSMG_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, ma, mb, p.sh, ep));
     return 0;
 }
@@ -1433,15 +1447,15 @@ template <int EPI>
 static inline int tc_launch(const TcContext& c, const TcPlan& p, const CUtensorMap& ma, const CUtensorMap& mb, bool mn,
                             const tc::EpiParams& ep, cudaStream_t s) {
 #define FSMG_GO(BN, MN)                                                                                                   \
-    (p.cl == 2 ? tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 2>, p, tc::SmemLayout<BN, 2>::TOTAL, ma, mb, ep, s)       \
-               : tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 1>, p, tc::SmemLayout<BN, 1>::TOTAL, ma, mb, ep, s))
+    (p.cl == 2 ? tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 2>, p, tc::SmemLayout<BN, 2>::TOTAL, ma, mb, ep, s, c.pdl) \
+               : tc_launch_kernel(tc::tc_gemm_kernel<BN, EPI, MN, MN, 1>, p, tc::SmemLayout<BN, 1>::TOTAL, ma, mb, ep, s, c.pdl))
     int rc = 0;
     if constexpr (EPI == tc::EPI_LSE || EPI == tc::EPI_SCATTER) {
         rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
     } else {
         if (p.bn == 512) {   // cta_group::2 only
-            rc = !mn ? tc_launch_kernel(tc::tc_gemm_kernel<512, EPI, false, false, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s)
-                     : tc_launch_kernel(tc::tc_gemm_kernel<512, EPI, true, true, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s);
+            rc = !mn ? tc_launch_kernel(tc::tc_gemm_kernel<512, EPI, false, false, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s, c.pdl)
+                     : tc_launch_kernel(tc::tc_gemm_kernel<512, EPI, true, true, 2>, p, tc::SmemLayout<512, 2>::TOTAL, ma, mb, ep, s, c.pdl);
         } else if (!mn) rc = (p.bn == 256) ? FSMG_GO(256, false) : FSMG_GO(128, false);
         else rc = (p.bn == 256) ? FSMG_GO(256, true) : FSMG_GO(128, true);
     }
