@@ -291,14 +291,33 @@ def measure_training(args, wname: str, w: dict, steps: int, warmup: int, world: 
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    # ---- device-resident arm: `value` ----------------------------------------------------------------
+    # Both arms run on a power-capped GPU whose SM clock keeps sinking for the first second of load (r3 visits: the second of two
+    # identical back-to-back passes is 1-3 % slower than the first).  The two end-to-end passes therefore BRACKET the
+    # device-resident arm — e2e pass, `value`, e2e pass — so that the drift falls on both numbers alike; the mean of the e2e passes
+    # is reported and both are listed.
     for i in range(warmup):
         eng.train_step_device(dev_batches[i % n_distinct])
+    for i in range(2):
+        model.train(host_batches[i % n_distinct])
     barrier()
     sampler = ClockSampler(local) if full else None
     if sampler:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    passes = []
+
+    def e2e_pass():
+        # every step synchronises on its loss, so host jitter (numpy block copies, the graph launch) is fully exposed
+        ev0.record()
+        for i in range(steps):
+            model.train(host_batches[i % n_distinct])   # numpy in -> pinned -> H2D -> step -> D2H loss -> float
+        ev1.record()
+        barrier()
+        passes.append(max_over_ranks(ev0.elapsed_time(ev1) / steps))
+
+    # ---- end-to-end arm through the plugin API with HOST buffers: `e2e`, first pass ---------------------
+    e2e_pass()
+    # ---- device-resident arm: `value` ----------------------------------------------------------------
     ev0.record()
     for i in range(steps):
         eng.train_step_device(dev_batches[(warmup + i) % n_distinct])
@@ -307,25 +326,12 @@ def measure_training(args, wname: str, w: dict, steps: int, warmup: int, world: 
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / steps)
     value = tokens_per_step / (ms_step * 1e-3)
     launches = eng.last_launch_count()
-
-    # ---- end-to-end arm through the plugin API with HOST buffers: `e2e` ------------------------------
-    for i in range(2):
-        model.train(host_batches[i % n_distinct])
-    barrier()
-    # every step synchronises on its loss, so host jitter (numpy block copies, the graph launch) is fully exposed: two
-    # passes of K steps each, the MEAN is reported and both are listed
-    passes = []
-    for _ in range(2):
-        ev0.record()
-        for i in range(steps):
-            model.train(host_batches[i % n_distinct])   # numpy in -> pinned -> H2D -> step -> D2H loss -> float
-        ev1.record()
-        barrier()
-        passes.append(max_over_ranks(ev0.elapsed_time(ev1) / steps))
-    clocks = sampler.stop() if sampler else None     # sampled across both timed regions (device-resident and end-to-end)
+    # ---- `e2e`, second pass --------------------------------------------------------------------------
+    e2e_pass()
+    clocks = sampler.stop() if sampler else None     # sampled across all three timed regions
     ms_e2e = float(np.mean(passes))
     e2e = dict(value=tokens_per_step / (ms_e2e * 1e-3), unit="tokens/s", ms_per_step=ms_e2e,
-               passes_ms_per_step=[round(x, 4) for x in passes], reported="mean of the passes",
+               passes_ms_per_step=[round(x, 4) for x in passes], reported="mean of the two passes, which bracket the device-resident arm",
                h2d_bytes_per_step=n_seqs * T * 4, d2h_bytes_per_step=16)
 
     if full:

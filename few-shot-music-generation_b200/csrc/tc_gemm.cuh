@@ -607,9 +607,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int e = 0; e < 16; ++e) csum[e] = 0.0f;
                 }
                 // Per-(row, chunk) scalars of a k block (chunk maximum; XF = 2 also the token's lse and target) come from global
-                // memory.  They are fetched TWO k blocks ahead, right after the arrive of the current one: a load still in flight
+                // memory.  They are fetched FOUR k blocks ahead, right after the arrive of the current one: a load still in flight
                 // would stall both its first use and the proxy fence (measured: 30 % of this loop's stall samples with a fetch
-                // one block ahead, issued before the wait) — this way every load has a whole k-block period to land.
+                // one block ahead issued before the wait; 16 % at the first use in the dWs kernel with two blocks — the chunk-maximum
+                // table comes from DRAM behind the 369 MB operand stream) — this way every load has three k-block periods to land.
                 struct XfOp { float cm, ls; int y; bool ok; };
                 auto fetch = [&](XfOp& o, int kb) {
                     o.cm = 0.0f; o.ls = 0.0f; o.y = -1; o.ok = false;
@@ -672,16 +673,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     }
                     if (++xstage == STAGES) { xstage = 0; xphase ^= 1; }
                 };
-                XfOp opA, opB;
+                XfOp opA, opB, opC, opD;
                 fetch(opA, kb0);
                 fetch(opB, kb0 + 1);
-                for (int kb = kb0; kb < kb1; kb += 2) {
+                fetch(opC, kb0 + 2);
+                fetch(opD, kb0 + 3);
+                for (int kb = kb0; kb < kb1; kb += 4) {
                     process(opA, kb);
-                    fetch(opA, kb + 2);
-                    if (kb + 1 < kb1) {
-                        process(opB, kb + 1);
-                        fetch(opB, kb + 3);
-                    }
+                    fetch(opA, kb + 4);
+                    if (kb + 1 < kb1) { process(opB, kb + 1); fetch(opB, kb + 5); }
+                    if (kb + 2 < kb1) { process(opC, kb + 2); fetch(opC, kb + 6); }
+                    if (kb + 3 < kb1) { process(opD, kb + 3); fetch(opD, kb + 7); }
                 }
                 if (XF == 2 && ep.xf_db != nullptr && n_blk == 0) {
                     // column sums over this piece's tokens: lanes of a warp that share (te & 3) hold the same columns for 8 tokens

@@ -19,6 +19,8 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_g
     python profiles/profile_step.py 1 > $out/${tag}_ncu_gemm.log 2>&1
 ncu -i $out/${tag}_gemm.ncu-rep --page raw --csv > $out/${tag}_gemm.raw.csv 2>/dev/null
 ncu -i $out/${tag}_gemm.ncu-rep --page source --csv --print-source sass > $out/${tag}_gemm.source.csv 2>/dev/null
+python profiles/stall_summary.py $out/${tag}_gemm.source.csv 14 > $out/${tag}_stalls_summary.md 2>&1
+[ "$KEEP_SOURCE_CSV" = "1" ] || rm -f $out/${tag}_gemm.source.csv
 python profiles/summarize_ncu.py $out/${tag}_gemm.ncu-rep > $out/${tag}_ncu_summary.md 2>&1
 rm -f $out/${tag}_*.ncu-rep
 tail -n 3 $out/${tag}_ncu_gemm.log
