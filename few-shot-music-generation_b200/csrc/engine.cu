@@ -524,7 +524,8 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
         XfArgs xf;
         xf.cmaxT = h->cmaxT; xf.ld_cmax = h->chunk_rows; xf.n_c16 = cdiv(h->V1, 16); xf.lse = h->lse; xf.y = h->y_ids; xf.row0 = r0; xf.db = nullptr;
         if (use_tc) {
-            // fused: logits tile -> online (max,sumexp) partials + target logit; fp16 logits only when training
+            // fused: logits tile -> online (max,sumexp) partials + target logit; when training also the fp16 chunk for the backward
+            // (exponentials + chunk maxima on the fused-softmax-gradient route, logits on the fallback route)
             int n_part = 0;
             {
                 ProfScope ps(h, PH_PROJ_FWD, s);
@@ -549,7 +550,7 @@ static int projection(fsmg_handle* h, int N, bool train, float loss_scale, float
             FSMG_LAUNCH_OK();
         }
         if (!train) continue;
-        // db_s += loss_scale * colsum(dlogits)   (the tcgen05 route fuses this into its softmax-grad pass)
+        // db_s += loss_scale * colsum(dlogits)   (the tcgen05 route sums it in the dWs GEMM's operand transform, or in its softmax-grad pass)
         if (!use_tc) {
             ProfScope ps(h, PH_SOFTMAX_GRAD, s);
             int rpb = 64;

@@ -5,13 +5,14 @@
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (default CL = 2: the leader CTA of a cluster of two issues ONE
 //                 tcgen05.mma.cta_group::2 of 256 x BN x 16 for the pair; CL = 1: UMMA 128 x BN x 16, cta_group::1)
 //   warps 2..17 : sixteen epilogue warps (TMEM lane quadrant x column quarter, tcgen05.ld 32x32b in 16-column chunks),
-//                 double-buffered TMEM accumulators (single-buffered for the 256 x 512 pair tiles)
+//                 double-buffered TMEM accumulators (single-buffered for the 256 x 512 pair tiles); in the XF instantiations the
+//                 same warps first transform the A operand of every k block in shared memory (fused softmax gradient, see below)
 // C[M,N] (op)= alpha * A * B^T with A, B each either K-major (row = m/n, contiguous k) or MN-major
 // (row = k, contiguous m/n) — the latter serves the weight-gradient contractions over tokens.
 //
 // Contractions of the hot path that run here: K3 input GEMM, K4 per-step recurrent GEMM
 // (until the persistent kernel takes over), K5+K7 projection with fused online log-sum-exp / NLL,
-// K8 dgrad / wgrad GEMMs.
+// K8 dgrad / wgrad GEMMs — for the projection's two, K7's softmax - onehot is rebuilt on their A operand (XF).
 #pragma once
 #include <type_traits>
 #include <cuda.h>
