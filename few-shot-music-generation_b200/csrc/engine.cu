@@ -776,7 +776,15 @@ static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
     const int TB = 256, H = h->H;
     const float a = 1.0f / 2048.0f;
     static const int SAMP_PDL = [] { const char* e = getenv("FSMG_SAMPLE_PDL"); return e ? atoi(e) : 0; }();
-    struct PdlScope { TcContext& c; PdlScope(TcContext& c_, int v) : c(c_) { c.pdl = v; } ~PdlScope() { c.pdl = 0; } } pdl_scope(h->tc, SAMP_PDL);
+    // 128-wide N tiles for the step's 256-row GEMMs (default; FSMG_SAMPLE_BN=256 restores the 256-wide plan): 32 / 37 tiles instead of
+    // 16 / 19, so the 74 CTA pairs are filled by a 2-way split of K with 8 MB of fp32 partial sums per GEMM instead of a 4.6-way
+    // stream-K split with 19 MB — measured 38.2 -> 35.2 us per 256-song decode step (gpurun_out r3f), token indices unchanged
+    static const int SAMP_NARROW = [] { const char* e = getenv("FSMG_SAMPLE_BN"); return e && atoi(e) == 256 ? 0 : 1; }();
+    struct PdlScope {
+        TcContext& c;
+        PdlScope(TcContext& c_, int v, int nw) : c(c_) { c.pdl = v; c.narrow = nw; }
+        ~PdlScope() { c.pdl = 0; c.narrow = 0; }
+    } pdl_scope(h->tc, SAMP_PDL, SAMP_NARROW);
     int rc;
     for (int l = 0; l < h->L; ++l) {
         // accumulating GEMMs into buffers their consumers (cell / argmax kernels) leave zeroed: no memset node per token

@@ -1249,6 +1249,7 @@ struct TcContext {
     int lstm_fks = 4;          // forward split kernel: K chunks per ring stage (FSMG_LSTM_FKS = 1, 2, 4)
     int lstm_rot = 3;          // rotated K-chunk order per loader in the recurrent kernels (bit 0: backward, bit 1: forward)
     int pdl = 0;               // launch with programmatic stream serialization (set by the decode loop around its GEMMs)
+    int narrow = 0;            // plan 128-wide N tiles even for wide N (set by the decode loop: FSMG_SAMPLE_BN=128)
     int xf_diag = 0;           // FSMG_XF_DIAG: timing diagnostics of the operand-transform GEMMs (results are wrong when set)
     int streamk = 1;           // stream-K scheduling of atomically-combined GEMMs when plain tiling quantises badly
     int lstm_reserve_sms = 0;  // SMs the persistent recurrent kernels leave free (for the NCCL kernels of an overlapped gradient all-reduce)
@@ -1376,7 +1377,7 @@ struct TcPlan {
 
 static inline TcPlan tc_plan(const TcContext& c, int M, int N, int K, bool allow_split, int cl_pref = 0, bool allow_wide = false) {
     TcPlan p;
-    p.bn = (N > 128) ? 256 : 128;
+    p.bn = (N > 128 && !c.narrow) ? 256 : 128;
     tc::GemmShape& sh = p.sh;
     sh.M = M; sh.N = N; sh.K = K;
     sh.n_m = cdiv(M, tc::BM);
