@@ -394,7 +394,7 @@ def measure_training(args, wname: str, w: dict, steps: int, warmup: int, world: 
     roof = {
         "recurrent_bwd": tensor_roofline("recurrent_bwd", "tc::lstm_bwd_* persistent reverse-time recurrence (dgates exchange, W_hh^T slice SMEM-resident)", rec_flops, rec_note),
         "recurrent_fwd": tensor_roofline("recurrent_fwd", "tc::lstm_fwd_* persistent recurrence (h exchange, W_hh slice SMEM-resident)", rec_flops, rec_note),
-        "proj_logits_lse": tensor_roofline("proj_logits_lse", "tc::tc_gemm_kernel<256, EPI_LSE> projection logits + online log-sum-exp", 2.0 * tok_gpu * h_ * v1_),
+        "proj_logits_lse": tensor_roofline("proj_logits_lse", "tc::tc_gemm_kernel<256, EPI_LSE> projection logits + online log-sum-exp" + (" (stores fp16 exponentials + chunk maxima for the fused softmax gradient)" if fused_sg else " (stores fp16 logits)"), 2.0 * tok_gpu * h_ * v1_),
         "proj_dh": tensor_roofline("proj_dh", "tc::tc_gemm_kernel<512" + (", XF=1> dH = (softmax - onehot rebuilt in smem) * Ws^T" if fused_sg else "> dH = dlogits * Ws^T"), 2.0 * tok_gpu * h_ * v1_),
         "proj_dws": tensor_roofline("proj_dws", "tc::tc_gemm_kernel<512, MN-major" + (", XF=2> dWs^T += (softmax - onehot rebuilt in smem)^T * hs, + bias gradient" if fused_sg else "> dWs^T += dlogits^T * hs"), 2.0 * tok_gpu * h_ * v1_),
     }
