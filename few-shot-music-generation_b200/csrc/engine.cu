@@ -777,8 +777,9 @@ static int sample_step_split(fsmg_handle* h, int n, cudaStream_t s) {
     const float a = 1.0f / 2048.0f;
     static const int SAMP_PDL = [] { const char* e = getenv("FSMG_SAMPLE_PDL"); return e ? atoi(e) : 0; }();
     // 128-wide N tiles for the step's 256-row GEMMs (default; FSMG_SAMPLE_BN=256 restores the 256-wide plan): 32 / 37 tiles instead of
-    // 16 / 19, so the 74 CTA pairs are filled by a 2-way split of K with 8 MB of fp32 partial sums per GEMM instead of a 4.6-way
-    // stream-K split with 19 MB — measured 38.2 -> 35.2 us per 256-song decode step (gpurun_out r3f), token indices unchanged
+    // 16 / 19, so the 74 CTA pairs are filled by a 2-way split of K with 8-10 MB of fp32 partial sums per GEMM instead of a 4-way
+    // split / 3.7-way stream-K cut with 17-18 MB — measured 38.2 -> 35.2 us per 256-song decode step (gpurun_out r3f), token indices
+    // unchanged (plans: fsmg_debug_plan, pinned in tests/test_abi_and_host.py)
     static const int SAMP_NARROW = [] { const char* e = getenv("FSMG_SAMPLE_BN"); return e && atoi(e) == 256 ? 0 : 1; }();
     struct PdlScope {
         TcContext& c;
@@ -1311,6 +1312,21 @@ int fsmg_debug_gemm(int32_t m, int32_t n, int32_t k, const void* d_a_f16, const 
     if (rc) return rc;
     if (!tc_gemm_supported(g, a_mn_major != 0, b_mn_major != 0)) return set_error(FSMG_ERR_INVALID, "shape unsupported by the tcgen05 GEMM");
     return tc_gemm(ctx, g, a_mn_major != 0, b_mn_major != 0, s);
+}
+
+// host-side planning of the tcgen05 GEMM core for a shape, without touching the device (defaults of a 148-SM B200): which tile
+// width, cluster size, K split / stream-K schedule and grid a launch would get.  out[0..7] = BN, cluster size, grid (CTAs),
+// M pair-tiles, N tiles, K splits, stream-K flag, k-block units per cluster.  narrow = the decode loop's 128-wide-tile request.
+// CPU tests pin the plans the design rests on (which shapes take the 256 x 512 pair tiles that carry the operand transform, how
+// the decode step's 256-row GEMMs are split) with it.
+int fsmg_debug_plan(int32_t m, int32_t n, int32_t k, int32_t allow_split, int32_t narrow, int32_t* out8) {
+    if (m <= 0 || n <= 0 || k <= 0 || !out8) return set_error(FSMG_ERR_INVALID, "fsmg_debug_plan: bad argument");
+    fsmg::TcContext ctx;              // defaults only: no driver call, no environment
+    ctx.narrow = narrow ? 1 : 0;
+    const TcPlan p = tc_plan(ctx, m, n, k, allow_split != 0, 0, true);
+    out8[0] = p.bn; out8[1] = p.cl; out8[2] = p.grid; out8[3] = p.sh.n_mp; out8[4] = p.sh.n_n; out8[5] = p.sh.n_s;
+    out8[6] = p.sh.streamk; out8[7] = p.sh.units_per_cluster;
+    return FSMG_OK;
 }
 
 // the two projection-backward GEMMs with the softmax gradient rebuilt on their A operand in shared memory (tc_gemm_kernel "XF"),

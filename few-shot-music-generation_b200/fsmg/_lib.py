@@ -70,6 +70,7 @@ SYMBOLS = {
     "fsmg_gather_token_rows": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
     "fsmg_unigram_step": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "fsmg_unigram_argmax": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "fsmg_debug_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "fsmg_debug_gemm_xf": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P, C.c_int32, _P, C.c_int64, _P, _P,
                                     C.c_float, _P, _P]),
     "fsmg_debug_softmax_grad": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _P, _P, _P, C.c_float, _P, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -197,6 +197,11 @@ int fsmg_debug_softmax_grad(int32_t rows, int32_t vocab1, int64_t ld, void* d_lo
                             const int32_t* d_y, float alpha, float* d_db, int32_t mode, int32_t param, int32_t waves,
                             void* stream);
 
+/* Host-side launch planning of the GEMM core for C[M,N] = A[M,K] * B[N,K]^T on a 148-SM B200, no device access (test hook).
+ * out8 = { N tile width, CTAs per cluster, grid size, M pair-tiles, N tiles, K splits, stream-K flag, k-block units per cluster }.
+ * allow_split: partial sums may be combined atomically (fp32 output, no accumulate); narrow: the decode loop's 128-wide tiles. */
+int fsmg_debug_plan(int32_t m, int32_t n, int32_t k, int32_t allow_split, int32_t narrow, int32_t* out8);
+
 /* The projection-backward GEMMs with the softmax gradient rebuilt on their A operand inside the kernel (no HBM pass; reference
  * lstm_baseline.py:70-75 + tf.gradients through sequence_loss and xw_plus_b), on caller-provided device buffers: test hook.
  * E holds exp(logit - max of the logit's 16-column chunk) in fp16, cmaxT[chunk, row] those maxima, lse/y the per-row

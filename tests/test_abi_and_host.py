@@ -63,6 +63,42 @@ def test_host_only_abi_param_layout(built_lib):
     lib.fsmg_destroy(h)
 
 
+def _plan(lib, m, n, k, split=1, narrow=0):
+    from fsmg import _lib
+    out = (C.c_int32 * 8)()
+    _lib.check(lib.fsmg_debug_plan(m, n, k, split, narrow, out))
+    return dict(zip(("bn", "cl", "grid", "m_tiles", "n_tiles", "k_splits", "streamk", "units"), list(out)))
+
+
+def test_gemm_plans_the_design_rests_on(built_lib):
+    """Host-side launch planning (csrc/tc_gemm.cuh tc_plan) for the shapes of BASELINE.json's configs, no device needed: which
+    GEMMs get the 256 x 512 cta_group::2 pair tiles — the only tiles that carry the operand transform of the fused softmax gradient
+    (DESIGN.md §5 G.c) — and how the decode step's 256-row GEMMs are cut (§5 S)."""
+    from fsmg import _lib
+    lib = _lib.load()
+    # configs[1]: 18 432-row chunk, H = 512, V' = 10 001
+    dh = _plan(lib, 18432, 512, 10001)
+    assert (dh["bn"], dh["cl"], dh["grid"], dh["m_tiles"], dh["k_splits"], dh["streamk"]) == (512, 2, 144, 72, 1, 0)   # 72 whole pair tiles, one wave
+    dws = _plan(lib, 10001, 512, 18432)
+    assert (dws["bn"], dws["cl"], dws["grid"], dws["streamk"]) == (512, 2, 148, 1) and dws["units"] * 74 >= 40 * 288   # stream-K over 40 x 288 k blocks
+    lse = _plan(lib, 18432, 10001, 512, split=0)
+    assert (lse["bn"], lse["cl"], lse["grid"], lse["m_tiles"], lse["n_tiles"], lse["k_splits"]) == (256, 2, 148, 72, 40, 1)
+    # one episode at the same model dimensions (what the reference trains per call) and configs[2] (H = 1024, V' = 4709): still pair tiles
+    assert _plan(lib, 5760, 512, 10001)["bn"] == 512 and _plan(lib, 10001, 512, 5760)["bn"] == 512
+    assert _plan(lib, 11520, 1024, 4709)["bn"] == 512 and _plan(lib, 4709, 1024, 11520)["bn"] == 512
+    # small models fall back to the in-place pass: no pair-tile plan
+    assert _plan(lib, 720, 64, 301)["bn"] != 512 and _plan(lib, 301, 64, 720)["bn"] != 512
+    # decode step (configs[4]: 256 songs, K = 3 x 1024 split-fp16): 128-wide tiles -> plain 2-way split of K that fills the 74 pairs
+    for n, tiles in ((4096, 32), (4709, 37)):
+        wide, narrow = _plan(lib, 256, n, 3072), _plan(lib, 256, n, 3072, narrow=1)
+        assert (narrow["bn"], narrow["n_tiles"], narrow["k_splits"], narrow["streamk"]) == (128, tiles, 2, 0)
+        assert narrow["grid"] == 2 * 2 * tiles and narrow["grid"] <= 148
+        assert wide["bn"] == 256 and (wide["k_splits"] >= 4 or wide["streamk"] == 1)
+        # bytes of fp32 partial tiles combined with REDs: splits x 256 x N x 4
+        cuts_wide = wide["k_splits"] if not wide["streamk"] else (wide["grid"] // 2) / wide["n_tiles"]
+        assert 2 * 256 * n * 4 < 0.6 * cuts_wide * 256 * n * 4
+
+
 def test_engine_refuses_to_run_without_cuda(built_lib):
     import torch
     if torch.cuda.is_available():
